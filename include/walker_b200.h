@@ -1,0 +1,203 @@
+/*
+ * walker_b200.h -- C ABI of libwalker_b200.so: the B200-native (sm_100a) hot path of
+ * De-Rosa/PPO-BipedalWalker -- the lockstep rigid-body physics step over N independent walkers and the
+ * PPO policy/value MLP forward / clipped-surrogate gradient / backward / Adam.
+ *
+ * The reference (C#/MonoGame) has no FFI boundary; its "operator API" for this path is the public method
+ * surface of Environment / Walker / Joint / RigidBody / IObject / IMaterial / PPOAgent / NeuralNetwork.
+ * Each export below names the reference method(s) it replaces (file:line relative to the reference root);
+ * INTEGRATION.md shows the P/Invoke stubs a maintainer adds on the C# side.
+ *
+ * Conventions
+ *   - every call returns int32 status (WB_OK == 0); wb_last_error() gives the message of the last failure
+ *     on the calling thread; nothing throws across the boundary.  The reference logs-and-continues
+ *     (RigidBody.cs:91-94, PPOAgent.cs:238-341); the host shim maps status != 0 to ErrorLogger.LogError.
+ *   - plain pointers + sizes only.  "host" pointers are ordinary (or pinned) CPU memory, copied inside
+ *     the call on the handle's stream and synchronised before returning.  "_dev" variants take DEVICE
+ *     pointers, enqueue on the handle's stream and return without synchronising.
+ *   - handles own all device state; a handle is bound to the device current at creation; not thread-safe
+ *     per handle, safe across handles.
+ *   - there is no CPU fallback: every compute entry fails with WB_ERR_NO_DEVICE without a CUDA device.
+ *
+ * State record ("identical start state" contract): per environment 92 floats + 2 int32,
+ *   f[ 0..57] vertices   LLL(6) LLU(6) Body(5) RLL(6) RLU(6), x/y interleaved   (Skeleton._vectors)
+ *   f[58..67] centroids  x/y per body (cached, never recomputed after Rotate: Skeleton.cs:89-97)
+ *   f[68..77] linear velocity x/y per body                                       (RigidBody.cs:30)
+ *   f[78..82] angular velocity, f[83..87] tracked angle                          (RigidBody.cs:31,33)
+ *   f[88..91] Joint._currentTorque                                               (Joint.cs:18)
+ *   i[0] flags: bit0-4 Collided(LLL,LLU,Body,RLL,RLU) bit5 Walker.Terminal bit6 floor-first list order
+ *   i[1] Environment._steps
+ * On the device the state is a structure of arrays: float state[92][N], int32 flags[N], int32 steps[N].
+ * wb_env_{get,set}_state use that same SoA layout on the host side ([92][N] floats, [2][N] ints).
+ */
+#ifndef WALKER_B200_H
+#define WALKER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB_OK 0
+#define WB_ERR_INVALID 1    /* bad argument                                   */
+#define WB_ERR_NO_DEVICE 2  /* no CUDA device / wrong architecture            */
+#define WB_ERR_CUDA 3       /* CUDA runtime error (message in wb_last_error)  */
+#define WB_ERR_UNSUPPORTED 4
+
+#define WB_STATE_FLOATS 92
+#define WB_STATE_INTS 2
+#define WB_OBS 12
+#define WB_ACT 4
+#define WB_PAIR_SLOTS 9
+
+#define WB_FLAG_TERMINAL (1 << 5)
+#define WB_FLAG_FLOOR_FIRST (1 << 6)
+
+/* built-in materials, Materials/{Ice,Wood,Paper,Titanium,Carpet,Rubber,Metal,SuperRubber}.cs:7-9 */
+enum { WB_ICE = 0, WB_WOOD, WB_PAPER, WB_TITANIUM, WB_CARPET, WB_RUBBER, WB_METAL, WB_SUPERRUBBER, WB_NUM_BUILTIN_MATERIALS };
+#define WB_MAX_MATERIALS 64
+
+typedef struct wb_env_batch wb_env_batch;
+typedef struct wb_policy wb_policy;
+
+/* Hyperparameters.cs:83-121 (only the fields the hot path reads). */
+typedef struct {
+  int32_t iterations;    /* :86  physics substeps per env-step (50)      */
+  int32_t max_timesteps; /* :87  (1000)                                  */
+  int32_t batch_size;    /* :111 divisor of the per-sample gradients (64)*/
+  int32_t use_gae;       /* :112                                         */
+  int32_t normalize_advantages; /* :113                                  */
+  float alpha, beta1, beta2, adam_epsilon; /* :104-107                   */
+  float gamma, lambda;   /* :116-117                                     */
+  float epsilon;         /* :120 PPO clip                                */
+  float log_std;         /* :121                                         */
+} wb_hyperparams;
+
+/* per ordered candidate pair per substep; slot = LLL:{0,1} LLU:{2,3} Body:{4} RLL:{5,6} RLU:{7,8},
+ * second index = position of the candidate in Environment._rigidBodies order (RigidBody.cs:66-96). */
+typedef struct {
+  int32_t other, aabb, sat, axis;
+  float nx, ny, depth;
+  int32_t ncontacts;
+  float c0x, c0y, c1x, c1y;
+} wb_pair_trace;
+
+typedef struct {
+  int32_t active;
+  float depth;
+} wb_joint_trace;
+
+/* ---- library ---- */
+const char* wb_version(void);
+int32_t wb_last_error(char* buf, size_t buf_len);
+/* selects the device (cudaSetDevice) and checks it is sm_100 */
+int32_t wb_init(int32_t device);
+int32_t wb_hyperparams_default(wb_hyperparams* hp); /* Hyperparameters.cs:83-121 defaults */
+/* new IMaterial implementation (Materials/IMaterial.cs:6-11) -> id usable in wb_env_create */
+int32_t wb_material_register(float inverse_mass, float restitution, float friction, int32_t* id_out);
+int32_t wb_material_get(int32_t id, float* inverse_mass, float* restitution, float* friction);
+
+/* ---- environments: Environment.cs / Walker/Walker.cs / Bodies / Objects ---- */
+/* new Environment(...) x N (Environment.cs:39-51: Walker ctor + CreateCreature + CreateFloor + InitialState).
+ * floor_material_ids / walker_material_ids: host arrays [n] or NULL (Metal floor Environment.cs:223, Carpet walker Walker.cs:30). */
+int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const uint8_t* walker_material_ids,
+                      const wb_hyperparams* hp, wb_env_batch** out);
+int32_t wb_env_destroy(wb_env_batch* env);
+int32_t wb_env_count(const wb_env_batch* env, int32_t* n_out);
+/* bind all work of this handle to a caller-owned cudaStream_t (NULL = default stream) */
+int32_t wb_env_set_stream(wb_env_batch* env, void* cuda_stream);
+int32_t wb_env_sync(wb_env_batch* env);
+
+/* Environment.Reset + Walker.Reset + InitialState (Environment.cs:167-180, Walker.cs:212-236) for envs whose
+ * mask byte != 0 (mask == NULL: all).  first_episode != 0 restores the constructor's list order instead. */
+int32_t wb_env_reset(wb_env_batch* env, const uint8_t* mask_host, int32_t first_episode);
+/* SoA blobs: state_f [92][N], state_i [2][N] (flags row, steps row) */
+int32_t wb_env_set_state(wb_env_batch* env, const float* state_f_host, const int32_t* state_i_host);
+int32_t wb_env_get_state(wb_env_batch* env, float* state_f_host, int32_t* state_i_host);
+
+/* Matrix.Clip(action,1,-1) + Walker.TakeActions + Joint.SetTorque (Environment.cs:78, Walker.cs:66-75, Joint.cs:56-61); actions [N][4] */
+int32_t wb_env_take_actions(wb_env_batch* env, const float* actions_host);
+/* Environment.StepObjects(deltaTime) (Environment.cs:126-143): deltaTime /= iterations; iterations x (4 Joint.Step + every IObject.Update) */
+int32_t wb_env_step_objects(wb_env_batch* env, float delta_time);
+/* same, recording every candidate pair / joint: pair_trace [N][iterations][9], joint_trace [N][iterations][4] (host) */
+int32_t wb_env_debug_contacts(wb_env_batch* env, float delta_time, wb_pair_trace* pair_trace_host,
+                              wb_joint_trace* joint_trace_host);
+/* tail of Environment.Step (Environment.cs:101-121): Walker.Update, CalculateReward (:148-154), terminal logic, Walker.GetState (Walker.cs:132-152).
+ * obs [N][12], reward [N], done [N] */
+int32_t wb_env_observe(wb_env_batch* env, float* obs_host, float* reward_host, uint8_t* done_host);
+/* Walker.GetState only */
+int32_t wb_env_get_obs(wb_env_batch* env, float* obs_host);
+
+/* Environment.Update minus the policy (Environment.cs:64-92): _steps++, TakeActions(Clip(a)), Step, and when
+ * auto_reset != 0 the Reset + InitialState that follows a terminal step (the returned obs is then the
+ * initial observation).  One fused kernel launch; host buffers, H2D/D2H inside the call. */
+int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_time, int32_t auto_reset, float* obs_host,
+                    float* reward_host, uint8_t* done_host);
+/* device-pointer variant: enqueue only (no copies, no sync) */
+int32_t wb_env_step_dev(wb_env_batch* env, const float* actions_dev, float delta_time, int32_t auto_reset, float* obs_dev,
+                        float* reward_dev, uint8_t* done_dev);
+/* number of kernel launches this handle has issued (bench.py "gpu_launches") */
+int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out);
+/* which kernel variant wb_env_step uses: lanes per environment (16 or 32); 0 = library default */
+int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env);
+
+/* ---- policy: Walker/PPO/PPOAgent.cs, Network/, Matrix.cs ---- */
+/* layer kinds of the network DSL (PPOAgent.ParseLayers, PPOAgent.cs:96-143) */
+enum { WB_DENSE = 0, WB_RELU = 1, WB_LEAKYRELU = 2, WB_TANH = 3 };
+
+/* new PPOAgent(stateSize, actionSize) (PPOAgent.cs:23-37) with already-parsed layer lists.
+ * Weights start at zero: load them with wb_policy_set_weights (Xavier init is host-side, Matrix.cs:59-80). */
+int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t* actor_kinds, const int32_t* actor_sizes,
+                         int32_t actor_layers, const int32_t* critic_kinds, const int32_t* critic_sizes, int32_t critic_layers,
+                         const wb_hyperparams* hp, wb_policy** out);
+int32_t wb_policy_destroy(wb_policy* p);
+int32_t wb_policy_set_stream(wb_policy* p, void* cuda_stream);
+int32_t wb_policy_sync(wb_policy* p);
+int32_t wb_policy_set_hyperparams(wb_policy* p, const wb_hyperparams* hp);
+/* flat parameter vectors, per dense layer W[out][in] row-major then b[out] (DenseLayer.Save, DenseLayer.cs:73-79). which: 0 actor, 1 critic */
+int32_t wb_policy_num_params(const wb_policy* p, int32_t which, int32_t* n_out);
+int32_t wb_policy_set_weights(wb_policy* p, int32_t which, const float* flat_host);
+int32_t wb_policy_get_weights(wb_policy* p, int32_t which, float* flat_host);
+int32_t wb_policy_get_grads(wb_policy* p, int32_t which, float* flat_host);
+/* Adam moments + per-dense-layer step counters (DenseLayer.cs:15-20) */
+int32_t wb_policy_get_adam(wb_policy* p, int32_t which, float* m_host, float* v_host, int32_t* iterations_host);
+int32_t wb_policy_set_adam(wb_policy* p, int32_t which, const float* m_host, const float* v_host, const int32_t* iterations_host);
+
+/* NeuralNetwork.FeedForward for n states (NeuralNetwork.cs:52-64): mean [n][act] (actor), value [n] (critic); either may be NULL */
+int32_t wb_policy_forward(wb_policy* p, int32_t n, const float* states_host, float* mean_host, float* value_host);
+int32_t wb_policy_forward_dev(wb_policy* p, int32_t n, const float* states_dev, float* mean_dev, float* value_dev);
+/* PPOAgent.SampleActions (PPOAgent.cs:381-398) with the two uniforms of each Box-Muller draw injected:
+ * uniforms [n][act][2] -> actions [n][act], logp [n][act] (NormalDistribution.cs:12-32) */
+int32_t wb_policy_sample(wb_policy* p, int32_t n, const float* states_host, const float* uniforms_host, float* actions_host,
+                         float* logp_host, float* mean_host);
+int32_t wb_policy_sample_dev(wb_policy* p, int32_t n, const float* states_dev, const float* uniforms_dev, float* actions_dev,
+                             float* logp_dev, float* mean_dev);
+/* same, uniforms from an on-device Philox-4x32-10 counter stream (seed, step): extension, the reference RNG is unseedable */
+int32_t wb_policy_sample_philox_dev(wb_policy* p, int32_t n, const float* states_dev, uint64_t seed, uint64_t step,
+                                    float* actions_dev, float* logp_dev, float* mean_dev);
+
+/* PPOAgent.Train(Batch) gradient part (PPOAgent.cs:218-342): Zero(), then for every sample the
+ * clipped-surrogate dL/dmu and 2(V-G)/B, back-propagated and accumulated; gradients stay on the device
+ * (wb_policy_get_grads).  n = samples in this call (this rank's shard); hp.batch_size is the divisor B.
+ * losses_host[2] = {sum g_V, sum mean_k g_mu} (the reference's "losses", PPOAgent.cs:331-332); skipped_host = samples skipped (:286-290). */
+int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
+                    const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host);
+int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
+                        const float* advantages_dev, const float* returns_dev);
+/* NeuralNetwork.Optimise -> DenseLayer.Adam on both networks (NeuralNetwork.cs:85-91, DenseLayer.cs:125-159) */
+int32_t wb_adam_step(wb_policy* p);
+/* device address + length of the contiguous gradient buffer [actor | critic | 2 loss sums | skipped] for the
+ * caller's all-reduce (NCCL over NVLink through torch.distributed, or wb_comm below) */
+int32_t wb_policy_grad_buffer(wb_policy* p, void** dev_ptr_out, int32_t* n_floats_out);
+int32_t wb_policy_launch_count(const wb_policy* p, int64_t* count_out);
+
+/* rollout -> update glue (PPOAgent.cs:414-498), one trajectory of length n on the device */
+int32_t wb_returns_advantages(wb_policy* p, int32_t n, const float* rewards_host, const float* values_host, float* returns_host,
+                              float* advantages_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WALKER_B200_H */

@@ -1,0 +1,11 @@
+"""walker_b200: B200-native (sm_100a) hot path of De-Rosa/PPO-BipedalWalker behind the reference's own
+Environment / Walker / IMaterial / PPOAgent method surface.  Imported as `ppo_bipedalwalker_b200`
+(see __graft_entry__.load_package); the compute lives in lib/libwalker_b200.so (csrc/), never in Python."""
+from ._lib import Hyperparams, WalkerB200Error, declared_symbols, lib  # noqa: F401
+from .env import (DT_FRAME, MATERIALS, Carpet, EnvBatch, Environment, Ice, IMaterial, Metal, Paper, Rubber,  # noqa: F401
+                  SuperRubber, Titanium, Walker, Wood, default_hyperparams, init, JOINT_TRACE_DTYPE, PAIR_TRACE_DTYPE)
+
+try:  # the policy half is optional only while the library is being brought up
+    from .ppo import *  # noqa: F401,F403
+except ImportError:  # pragma: no cover
+    pass

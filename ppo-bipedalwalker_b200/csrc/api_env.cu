@@ -1,0 +1,451 @@
+// api_env.cu -- C ABI for the environment batch (include/walker_b200.h): handles, materials, scene construction,
+// host<->device staging.  All compute is in physics.cu; there is no CPU path.
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.h"
+#include "physics.cuh"
+
+namespace wb {
+
+static thread_local char g_err[512] = "";
+char* last_error_buffer() { return g_err; }
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int32_t require_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(WB_ERR_NO_DEVICE, "no CUDA device: %s (libwalker_b200 has no CPU fallback)", cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(WB_ERR_NO_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(WB_ERR_NO_DEVICE, "device %d is sm_%d%d; libwalker_b200 is built for sm_100a only", dev, prop.major, prop.minor);
+  return WB_OK;
+}
+
+// ------------------------------------------------------------------ materials (Materials/*.cs, IMaterial.cs:6-11)
+static std::mutex g_mat_mutex;
+static Material g_materials[WB_MAX_MATERIALS] = {
+    {11.0f, 0.3f, 0.0f},   // Ice
+    {20.0f, 0.3f, 0.01f},  // Wood
+    {1.0f, 0.3f, 0.1f},    // Paper
+    {0.01f, 0.1f, 0.2f},   // Titanium
+    {5.0f, 0.3f, 0.8f},    // Carpet
+    {11.0f, 0.7f, 0.5f},   // Rubber
+    {15.0f, 0.3f, 1.0f},   // Metal
+    {11.0f, 1.0f, 1.0f},   // SuperRubber
+};
+static int g_material_count = WB_NUM_BUILTIN_MATERIALS;
+
+// ------------------------------------------------------------------ scene constants, host restatement in strict fp32
+// (volatile stores keep every intermediate in binary32 and stop the host compiler from contracting)
+static inline float f_add(float a, float b) { volatile float r = a + b; return r; }
+static inline float f_sub(float a, float b) { volatile float r = a - b; return r; }
+static inline float f_mul(float a, float b) { volatile float r = a * b; return r; }
+static inline float f_div(float a, float b) { volatile float r = a / b; return r; }
+
+// Skeleton.FindCentroid (Skeleton.cs:100-113): sum, then Vector2 / count = multiply by (1f / count)
+static void centroid_of(const float* v, int n, float* out) {
+  float sx = 0.0f, sy = 0.0f;
+  for (int i = 0; i < n; i++) {
+    sx = f_add(sx, v[2 * i]);
+    sy = f_add(sy, v[2 * i + 1]);
+  }
+  const float factor = f_div(1.0f, (float)n);
+  out[0] = f_mul(sx, factor);
+  out[1] = f_mul(sy, factor);
+}
+
+// Pole.FromSize (Pole.cs:18-34)
+static void pole_from_size(float cx, float cy, float size, float* v12) {
+  const float adjustment = f_mul((float)0.1, size);
+  const float h = f_mul(adjustment, 3.5f);
+  const float xs[6] = {f_add(cx, adjustment), cx, f_sub(cx, adjustment), f_sub(cx, adjustment), cx, f_add(cx, adjustment)};
+  const float ys[6] = {f_add(cy, h), f_add(cy, h), f_add(cy, h), f_sub(cy, h), f_sub(cy, h), f_sub(cy, h)};
+  for (int i = 0; i < 6; i++) {
+    v12[2 * i] = xs[i];
+    v12[2 * i + 1] = ys[i];
+  }
+}
+
+// Walker ctor + CreateBodies (Walker.cs:25-34,155-177) and Environment.CreateFloor (Environment.cs:211-226)
+static void build_scene_constants(float* init92, float* floor10) {
+  const float px = 125.0f, py = 800.0f;  // Walker._position, Walker.cs:31
+  float verts[58];
+  float* lll = verts;
+  float* llu = verts + 12;
+  float* body = verts + 24;
+  float* rll = verts + 34;
+  float* rlu = verts + 46;
+  const float hull[10] = {f_add(px, 20.f), f_add(py, 20.f), px, f_add(py, 20.f), f_sub(px, 20.f), f_add(py, 20.f),
+                          f_sub(px, 20.f), f_sub(py, 20.f), f_add(px, 20.f), f_sub(py, 20.f)};
+  memcpy(body, hull, sizeof(hull));
+  pole_from_size(f_add(px, 0.f), f_add(py, 30.f), 75.f, llu);
+  pole_from_size(f_add(px, 0.f), f_add(py, 60.f), 75.f, lll);
+  pole_from_size(f_add(px, 0.f), f_add(py, 30.f), 75.f, rlu);
+  pole_from_size(f_add(px, 0.f), f_add(py, 60.f), 75.f, rll);
+  memset(init92, 0, sizeof(float) * kStateFloats);
+  memcpy(init92, verts, sizeof(verts));
+  centroid_of(lll, 6, init92 + 58);
+  centroid_of(llu, 6, init92 + 60);
+  centroid_of(body, 5, init92 + 62);
+  centroid_of(rll, 6, init92 + 64);
+  centroid_of(rlu, 6, init92 + 66);
+  const float fl[8] = {-50.f, 1050.f, -50.f, 900.f, 1050.f, 900.f, 1050.f, 1050.f};
+  memcpy(floor10, fl, sizeof(fl));
+  centroid_of(fl, 4, floor10 + 8);
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+struct wb_env_batch {
+  int32_t n = 0, n_pad = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  wb_hyperparams hp{};
+  int lanes = 16;
+  int64_t launches = 0;
+  // device state (structure of arrays)
+  float* d_state = nullptr;    // [92][n_pad]
+  int32_t* d_flags = nullptr;  // [n_pad]
+  int32_t* d_steps = nullptr;  // [n_pad]
+  float* d_pos = nullptr;      // [2][n_pad]
+  uint8_t* d_floor_mat = nullptr;
+  uint8_t* d_walker_mat = nullptr;
+  // device I/O staging for the host-pointer entry points
+  float* d_actions = nullptr;  // [n][4]
+  float* d_obs = nullptr;      // [n][12]
+  float* d_reward = nullptr;   // [n]
+  uint8_t* d_done = nullptr;   // [n]
+  uint8_t* d_mask = nullptr;   // [n]
+  float init92[WB_STATE_FLOATS];
+};
+
+extern "C" {
+
+const char* wb_version(void) { return "walker_b200 0.1.0 (sm_100a)"; }
+
+int32_t wb_last_error(char* buf, size_t buf_len) {
+  if (!buf || buf_len == 0) return WB_ERR_INVALID;
+  strncpy(buf, last_error_buffer(), buf_len - 1);
+  buf[buf_len - 1] = 0;
+  return WB_OK;
+}
+
+int32_t wb_init(int32_t device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(WB_ERR_NO_DEVICE, "cudaSetDevice(%d): %s (libwalker_b200 has no CPU fallback)", device, cudaGetErrorString(e));
+  }
+  return require_device();
+}
+
+int32_t wb_hyperparams_default(wb_hyperparams* hp) {
+  WB_REQUIRE(hp, "hp is null");
+  hp->iterations = 50;
+  hp->max_timesteps = 1000;
+  hp->batch_size = 64;
+  hp->use_gae = 0;
+  hp->normalize_advantages = 0;
+  hp->alpha = 0.001f;
+  hp->beta1 = 0.9f;
+  hp->beta2 = 0.999f;
+  hp->adam_epsilon = 1e-8f;
+  hp->gamma = 0.9f;
+  hp->lambda = 0.95f;
+  hp->epsilon = 0.3f;
+  hp->log_std = -1.0f;
+  return WB_OK;
+}
+
+int32_t wb_material_register(float inverse_mass, float restitution, float friction, int32_t* id_out) {
+  WB_REQUIRE(id_out, "id_out is null");
+  std::lock_guard<std::mutex> lock(g_mat_mutex);
+  if (g_material_count >= WB_MAX_MATERIALS) return fail(WB_ERR_INVALID, "material table full (%d)", WB_MAX_MATERIALS);
+  g_materials[g_material_count] = Material{inverse_mass, restitution, friction};
+  *id_out = g_material_count++;
+  return WB_OK;
+}
+
+int32_t wb_material_get(int32_t id, float* inverse_mass, float* restitution, float* friction) {
+  std::lock_guard<std::mutex> lock(g_mat_mutex);
+  if (id < 0 || id >= g_material_count) return fail(WB_ERR_INVALID, "unknown material id %d", id);
+  if (inverse_mass) *inverse_mass = g_materials[id].inverse_mass;
+  if (restitution) *restitution = g_materials[id].restitution;
+  if (friction) *friction = g_materials[id].friction;
+  return WB_OK;
+}
+
+static int32_t launch(wb_env_batch* env, int phases, float dt, const float* d_actions, float* d_obs, float* d_reward,
+                      uint8_t* d_done, const uint8_t* d_mask, wb_pair_trace* d_pt, wb_joint_trace* d_jt) {
+  PhysicsParams p{};
+  p.state = env->d_state;
+  p.flags = env->d_flags;
+  p.steps = env->d_steps;
+  p.pos = env->d_pos;
+  p.floor_mat = env->d_floor_mat;
+  p.walker_mat = env->d_walker_mat;
+  p.actions = d_actions;
+  p.reset_mask = d_mask;
+  p.obs = d_obs;
+  p.reward = d_reward;
+  p.done = d_done;
+  p.pair_trace = d_pt;
+  p.joint_trace = d_jt;
+  p.n = env->n;
+  p.n_pad = env->n_pad;
+  p.dt = dt;
+  p.iterations = env->hp.iterations;
+  p.max_timesteps = env->hp.max_timesteps;
+  p.phases = phases;
+  WB_CUDA(launch_physics(p, env->lanes, d_pt != nullptr || d_jt != nullptr, env->stream));
+  env->launches++;
+  return WB_OK;
+}
+
+int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const uint8_t* walker_material_ids,
+                      const wb_hyperparams* hp, wb_env_batch** out) {
+  WB_REQUIRE(out, "out is null");
+  *out = nullptr;
+  WB_REQUIRE(n_envs > 0, "n_envs must be positive");
+  if (int32_t rc = require_device()) return rc;
+  wb_env_batch* env = new (std::nothrow) wb_env_batch();
+  WB_REQUIRE(env, "out of host memory");
+  cudaGetDevice(&env->device);
+  env->n = n_envs;
+  env->n_pad = (n_envs + kEnvsPerCta - 1) / kEnvsPerCta * kEnvsPerCta;
+  if (hp) env->hp = *hp; else wb_hyperparams_default(&env->hp);
+  if (env->hp.iterations <= 0 || env->hp.iterations >= 200) {  // Hyperparameters.cs:189-217 range check
+    delete env;
+    return fail(WB_ERR_INVALID, "iterations must be in (0, 200)");
+  }
+  const size_t np = (size_t)env->n_pad;
+  std::vector<uint8_t> fm(np, (uint8_t)WB_METAL), wm(np, (uint8_t)WB_CARPET);
+  {
+    std::lock_guard<std::mutex> lock(g_mat_mutex);
+    for (int i = 0; i < n_envs; i++) {
+      if (floor_material_ids) fm[i] = floor_material_ids[i];
+      if (walker_material_ids) wm[i] = walker_material_ids[i];
+      if (fm[i] >= g_material_count || wm[i] >= g_material_count) {
+        delete env;
+        return fail(WB_ERR_INVALID, "env %d uses an unregistered material id", i);
+      }
+    }
+    WB_CUDA(upload_materials(g_materials, WB_MAX_MATERIALS));
+  }
+  float floor10[10];
+  build_scene_constants(env->init92, floor10);
+  WB_CUDA(upload_scene_constants(env->init92, floor10));
+  WB_CUDA(cudaMalloc(&env->d_state, sizeof(float) * kStateFloats * np));
+  WB_CUDA(cudaMalloc(&env->d_flags, sizeof(int32_t) * np));
+  WB_CUDA(cudaMalloc(&env->d_steps, sizeof(int32_t) * np));
+  WB_CUDA(cudaMalloc(&env->d_pos, sizeof(float) * 2 * np));
+  WB_CUDA(cudaMalloc(&env->d_floor_mat, np));
+  WB_CUDA(cudaMalloc(&env->d_walker_mat, np));
+  WB_CUDA(cudaMalloc(&env->d_actions, sizeof(float) * WB_ACT * np));
+  WB_CUDA(cudaMalloc(&env->d_obs, sizeof(float) * WB_OBS * np));
+  WB_CUDA(cudaMalloc(&env->d_reward, sizeof(float) * np));
+  WB_CUDA(cudaMalloc(&env->d_done, np));
+  WB_CUDA(cudaMalloc(&env->d_mask, np));
+  WB_CUDA(cudaMemset(env->d_state, 0, sizeof(float) * kStateFloats * np));
+  WB_CUDA(cudaMemset(env->d_flags, 0, sizeof(int32_t) * np));
+  WB_CUDA(cudaMemset(env->d_steps, 0, sizeof(int32_t) * np));
+  WB_CUDA(cudaMemset(env->d_pos, 0, sizeof(float) * 2 * np));
+  WB_CUDA(cudaMemcpy(env->d_floor_mat, fm.data(), np, cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMemcpy(env->d_walker_mat, wm.data(), np, cudaMemcpyHostToDevice));
+  // constructor state: walker first, floor last (Environment.cs:46-48), then InitialState
+  if (int32_t rc = launch(env, kPhaseResetMasked | kPhaseFirstEpisode, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) {
+    wb_env_destroy(env);
+    return rc;
+  }
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  *out = env;
+  return WB_OK;
+}
+
+int32_t wb_env_destroy(wb_env_batch* env) {
+  if (!env) return WB_OK;
+  cudaFree(env->d_state);
+  cudaFree(env->d_flags);
+  cudaFree(env->d_steps);
+  cudaFree(env->d_pos);
+  cudaFree(env->d_floor_mat);
+  cudaFree(env->d_walker_mat);
+  cudaFree(env->d_actions);
+  cudaFree(env->d_obs);
+  cudaFree(env->d_reward);
+  cudaFree(env->d_done);
+  cudaFree(env->d_mask);
+  delete env;
+  return WB_OK;
+}
+
+int32_t wb_env_count(const wb_env_batch* env, int32_t* n_out) {
+  WB_REQUIRE(env && n_out, "null argument");
+  *n_out = env->n;
+  return WB_OK;
+}
+
+int32_t wb_env_set_stream(wb_env_batch* env, void* cuda_stream) {
+  WB_REQUIRE(env, "env is null");
+  env->stream = (cudaStream_t)cuda_stream;
+  return WB_OK;
+}
+
+int32_t wb_env_sync(wb_env_batch* env) {
+  WB_REQUIRE(env, "env is null");
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  return WB_OK;
+}
+
+int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out) {
+  WB_REQUIRE(env && count_out, "null argument");
+  *count_out = env->launches;
+  return WB_OK;
+}
+
+int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env) {
+  WB_REQUIRE(env, "env is null");
+  if (lanes_per_env == 0) lanes_per_env = 16;
+  if (lanes_per_env != 16 && lanes_per_env != 32) return fail(WB_ERR_INVALID, "lanes_per_env must be 16 or 32");
+  env->lanes = lanes_per_env;
+  return WB_OK;
+}
+
+int32_t wb_env_reset(wb_env_batch* env, const uint8_t* mask_host, int32_t first_episode) {
+  WB_REQUIRE(env, "env is null");
+  const uint8_t* d_mask = nullptr;
+  if (mask_host) {
+    WB_CUDA(cudaMemcpyAsync(env->d_mask, mask_host, env->n, cudaMemcpyHostToDevice, env->stream));
+    d_mask = env->d_mask;
+  }
+  if (int32_t rc = launch(env, kPhaseResetMasked | (first_episode ? kPhaseFirstEpisode : 0), 0.f, nullptr, nullptr, nullptr,
+                          nullptr, d_mask, nullptr, nullptr))
+    return rc;
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  return WB_OK;
+}
+
+int32_t wb_env_set_state(wb_env_batch* env, const float* state_f_host, const int32_t* state_i_host) {
+  WB_REQUIRE(env && state_f_host && state_i_host, "null argument");
+  const size_t n = env->n, np = env->n_pad;
+  WB_CUDA(cudaMemcpy2DAsync(env->d_state, np * sizeof(float), state_f_host, n * sizeof(float), n * sizeof(float), kStateFloats,
+                            cudaMemcpyHostToDevice, env->stream));
+  WB_CUDA(cudaMemcpyAsync(env->d_flags, state_i_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, env->stream));
+  WB_CUDA(cudaMemcpyAsync(env->d_steps, state_i_host + n, n * sizeof(int32_t), cudaMemcpyHostToDevice, env->stream));
+  // Walker._position == Body centroid at every step boundary (Walker.cs:52): rows 62/63 of the record
+  WB_CUDA(cudaMemcpyAsync(env->d_pos, env->d_state + 62 * np, np * sizeof(float), cudaMemcpyDeviceToDevice, env->stream));
+  WB_CUDA(cudaMemcpyAsync(env->d_pos + np, env->d_state + 63 * np, np * sizeof(float), cudaMemcpyDeviceToDevice, env->stream));
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  return WB_OK;
+}
+
+int32_t wb_env_get_state(wb_env_batch* env, float* state_f_host, int32_t* state_i_host) {
+  WB_REQUIRE(env && state_f_host && state_i_host, "null argument");
+  const size_t n = env->n, np = env->n_pad;
+  WB_CUDA(cudaMemcpy2DAsync(state_f_host, n * sizeof(float), env->d_state, np * sizeof(float), n * sizeof(float), kStateFloats,
+                            cudaMemcpyDeviceToHost, env->stream));
+  WB_CUDA(cudaMemcpyAsync(state_i_host, env->d_flags, n * sizeof(int32_t), cudaMemcpyDeviceToHost, env->stream));
+  WB_CUDA(cudaMemcpyAsync(state_i_host + n, env->d_steps, n * sizeof(int32_t), cudaMemcpyDeviceToHost, env->stream));
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  return WB_OK;
+}
+
+int32_t wb_env_take_actions(wb_env_batch* env, const float* actions_host) {
+  WB_REQUIRE(env && actions_host, "null argument");
+  WB_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, sizeof(float) * WB_ACT * env->n, cudaMemcpyHostToDevice, env->stream));
+  if (int32_t rc = launch(env, kPhaseTakeActions, 0.f, env->d_actions, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) return rc;
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  return WB_OK;
+}
+
+int32_t wb_env_step_objects(wb_env_batch* env, float delta_time) {
+  WB_REQUIRE(env, "env is null");
+  if (int32_t rc = launch(env, kPhaseStepObjects, delta_time, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) return rc;
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  return WB_OK;
+}
+
+int32_t wb_env_debug_contacts(wb_env_batch* env, float delta_time, wb_pair_trace* pair_trace_host,
+                              wb_joint_trace* joint_trace_host) {
+  WB_REQUIRE(env && pair_trace_host && joint_trace_host, "null argument");
+  const size_t npair = (size_t)env->n * env->hp.iterations * WB_PAIR_SLOTS;
+  const size_t njoint = (size_t)env->n * env->hp.iterations * 4;
+  wb_pair_trace* d_pt = nullptr;
+  wb_joint_trace* d_jt = nullptr;
+  WB_CUDA(cudaMalloc(&d_pt, npair * sizeof(wb_pair_trace)));
+  cudaError_t e = cudaMalloc(&d_jt, njoint * sizeof(wb_joint_trace));
+  if (e != cudaSuccess) {
+    cudaFree(d_pt);
+    return fail(WB_ERR_CUDA, "cudaMalloc(joint trace): %s", cudaGetErrorString(e));
+  }
+  int32_t rc = launch(env, kPhaseStepObjects, delta_time, nullptr, nullptr, nullptr, nullptr, nullptr, d_pt, d_jt);
+  if (rc == WB_OK) {
+    e = cudaMemcpyAsync(pair_trace_host, d_pt, npair * sizeof(wb_pair_trace), cudaMemcpyDeviceToHost, env->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(joint_trace_host, d_jt, njoint * sizeof(wb_joint_trace), cudaMemcpyDeviceToHost, env->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(env->stream);
+    if (e != cudaSuccess) rc = fail(WB_ERR_CUDA, "trace copy: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_pt);
+  cudaFree(d_jt);
+  return rc;
+}
+
+static int32_t copy_out(wb_env_batch* env, float* obs_host, float* reward_host, uint8_t* done_host) {
+  if (obs_host) WB_CUDA(cudaMemcpyAsync(obs_host, env->d_obs, sizeof(float) * WB_OBS * env->n, cudaMemcpyDeviceToHost, env->stream));
+  if (reward_host) WB_CUDA(cudaMemcpyAsync(reward_host, env->d_reward, sizeof(float) * env->n, cudaMemcpyDeviceToHost, env->stream));
+  if (done_host) WB_CUDA(cudaMemcpyAsync(done_host, env->d_done, env->n, cudaMemcpyDeviceToHost, env->stream));
+  WB_CUDA(cudaStreamSynchronize(env->stream));
+  return WB_OK;
+}
+
+int32_t wb_env_observe(wb_env_batch* env, float* obs_host, float* reward_host, uint8_t* done_host) {
+  WB_REQUIRE(env, "env is null");
+  if (int32_t rc = launch(env, kPhaseObserve, 0.f, nullptr, env->d_obs, env->d_reward, env->d_done, nullptr, nullptr, nullptr)) return rc;
+  return copy_out(env, obs_host, reward_host, done_host);
+}
+
+int32_t wb_env_get_obs(wb_env_batch* env, float* obs_host) {
+  WB_REQUIRE(env && obs_host, "null argument");
+  if (int32_t rc = launch(env, kPhaseObsOnly, 0.f, nullptr, env->d_obs, nullptr, nullptr, nullptr, nullptr, nullptr)) return rc;
+  return copy_out(env, obs_host, nullptr, nullptr);
+}
+
+static int step_phases(int32_t auto_reset) {
+  return kPhaseIncSteps | kPhaseTakeActions | kPhaseStepObjects | kPhaseObserve | (auto_reset ? kPhaseAutoReset : 0);
+}
+
+int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_time, int32_t auto_reset, float* obs_host,
+                    float* reward_host, uint8_t* done_host) {
+  WB_REQUIRE(env && actions_host, "null argument");
+  WB_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, sizeof(float) * WB_ACT * env->n, cudaMemcpyHostToDevice, env->stream));
+  if (int32_t rc = launch(env, step_phases(auto_reset), delta_time, env->d_actions, env->d_obs, env->d_reward, env->d_done, nullptr,
+                          nullptr, nullptr))
+    return rc;
+  return copy_out(env, obs_host, reward_host, done_host);
+}
+
+int32_t wb_env_step_dev(wb_env_batch* env, const float* actions_dev, float delta_time, int32_t auto_reset, float* obs_dev,
+                        float* reward_dev, uint8_t* done_dev) {
+  WB_REQUIRE(env && actions_dev && obs_dev && reward_dev && done_dev, "null argument");
+  return launch(env, step_phases(auto_reset), delta_time, actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, nullptr);
+}
+
+}  // extern "C"

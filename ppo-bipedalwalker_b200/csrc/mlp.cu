@@ -1,0 +1,512 @@
+// mlp.cu -- PPO policy/value MLP kernels for sm_100a (fp32 CUDA-core version of the fused pipeline).
+//
+// Replaces the reference's per-sample Matrix-library pipeline (Walker/PPO/Matrix.cs, Network/DenseLayer.cs,
+// Network/ActivationLayer.cs, PPOAgent.cs:218-346,381-398, NormalDistribution.cs) with batched kernels:
+//
+//   ppo_fused_kernel  persistent CTAs; each iteration stages a tile of 64 samples in shared memory and runs
+//                     actor + critic forward, the per-sample clipped-surrogate gradient (Appendix B of
+//                     SURVEY.md), and the full backward pass as tile GEMMs; weight-gradient tiles are held in
+//                     registers across all tiles of the CTA and written once as a per-CTA partial.
+//   reduce_partials   deterministic fixed-order sum of the per-CTA partials (no atomics) -> gradient buffer.
+//   adam_kernel       DenseLayer.Adam (DenseLayer.cs:125-159) with the reference's operation order.
+//   returns_kernel    Monte-Carlo return / the reference's GAE variant / Normalize (PPOAgent.cs:414-498).
+//
+// Dot products accumulate in the reference's left-to-right order (Matrix.Multiply, Matrix.cs:604-616) with
+// fused multiply-add; the cross-sample sum of dW is tiled (per CTA, then across CTAs) instead of the
+// reference's strictly sequential per-sample accumulation -- covered by the 1e-4 relative tolerance.
+#include "mlp.cuh"
+
+#include <cfloat>
+
+namespace wb {
+
+constexpr int kPad = 68;  // row stride (floats) of [*][64] tiles in shared memory: float4-aligned, bank-staggered
+
+struct __align__(16) MlpSmem {
+  float W1[kHid * kIn];
+  float W2[kHid * kPad];
+  float W3[kAct * kPad];
+  float Wc1[kHid * kIn];
+  float Wc2[kHid];
+  float b1[kHid], b2[kHid], bc1[kHid];
+  float b3[kAct], bc2[4];
+  float X[kTile * kIn];
+  float A1[kTile * kPad], A2[kTile * kPad], C1[kTile * kPad];   // post-activation hidden layers
+  float G2[kTile * kPad], G1[kTile * kPad], Gc1[kTile * kPad];  // dL/dz of the hidden layers
+  float MU[kTile * kAct], G3[kTile * kAct], V[kTile], GV[kTile];
+  float red[kMlpThreads];
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// ActivationLayer.cs:46-59
+__device__ __forceinline__ float leaky(float v) { return fmaxf(0.2f * v, v); }
+__device__ __forceinline__ float leaky_grad_from_output(float a) { return a < 0.0f ? 0.2f : 1.0f; }  // sign(a) == sign(z)
+
+// out[s][o] = act(sum_i in[s][i] * W[o][i] + b[o]) for a 64-sample x 64-output tile; thread = 4 samples x 4 outputs
+template <int K, int LDIN, int LDW>
+__device__ __forceinline__ void dense64_forward(const float* in, const float* W, const float* b, float* out) {
+  const int ts = threadIdx.x >> 4, to = threadIdx.x & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[k][j] = 0.0f;
+#pragma unroll 4
+  for (int i = 0; i < K; i += 4) {
+    float4 a[4], w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) a[k] = ld4(in + (ts * 4 + k) * LDIN + i);
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = ld4(W + (to + 16 * j) * LDW + i);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        acc[k][j] = fmaf(a[k].x, w[j].x, acc[k][j]);
+        acc[k][j] = fmaf(a[k].y, w[j].y, acc[k][j]);
+        acc[k][j] = fmaf(a[k].z, w[j].z, acc[k][j]);
+        acc[k][j] = fmaf(a[k].w, w[j].w, acc[k][j]);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int o = to + 16 * j;
+      out[(ts * 4 + k) * kPad + o] = leaky(acc[k][j] + b[o]);
+    }
+}
+
+// Philox-4x32-10 (counter-based; extension -- the reference's System.Random is unseedable)
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// NormalDistribution.LogProbabilityDensity, NormalDistribution.cs:24-32 (-ln(std) and ln(sqrt(2pi)) precomputed on the host)
+__device__ __forceinline__ float log_prob(float mean, float stdv, float action, float neg_log_std, float log_sqrt_2pi) {
+  float fraction = (action - mean) / stdv;
+  fraction *= fraction;
+  fraction /= 2.0f;
+  return neg_log_std - log_sqrt_2pi - fraction;
+}
+
+struct GradConsts {
+  float stdv, neg_log_std, log_sqrt_2pi, upper, lower, variance;
+};
+
+__global__ void __launch_bounds__(kMlpThreads, 1) ppo_fused_kernel(const MlpParams p, const GradConsts gc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MlpSmem& S = *reinterpret_cast<MlpSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+
+  // ---- weights -> shared memory (padded rows)
+  for (int i = tid; i < kHid * kIn; i += kMlpThreads) {
+    S.W1[i] = p.params[kOffW1 + i];
+    S.Wc1[i] = p.params[kOffWc1 + i];
+  }
+  for (int i = tid; i < kHid * kHid; i += kMlpThreads) S.W2[(i >> 6) * kPad + (i & 63)] = p.params[kOffW2 + i];
+  for (int i = tid; i < kAct * kHid; i += kMlpThreads) S.W3[(i >> 6) * kPad + (i & 63)] = p.params[kOffW3 + i];
+  if (tid < kHid) {
+    S.b1[tid] = p.params[kOffB1 + tid];
+    S.b2[tid] = p.params[kOffB2 + tid];
+    S.bc1[tid] = p.params[kOffBc1 + tid];
+    S.Wc2[tid] = p.params[kOffWc2 + tid];
+  }
+  if (tid < kAct) S.b3[tid] = p.params[kOffB3 + tid];
+  if (tid == 0) S.bc2[0] = p.params[kOffBc2];
+
+  const bool grad = p.mode == kModeGrad;
+  // weight-gradient accumulators, resident in registers across every tile this CTA processes
+  float accW2[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int l = 0; l < 4; l++) accW2[j][l] = 0.0f;
+  float accW1[3] = {0.f, 0.f, 0.f}, accWc1[3] = {0.f, 0.f, 0.f};
+  float accW3 = 0.0f, accS = 0.0f, accT = 0.0f;
+  float lossV = 0.0f, lossA = 0.0f, skipped = 0.0f;
+
+  const int ntiles = (p.n + kTile - 1) / kTile;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int s0 = tile * kTile;
+    const int nvalid = min(kTile, p.n - s0);
+    __syncthreads();  // previous tile fully consumed (also orders the weight staging on the first pass)
+    for (int i = tid; i < kTile * kIn; i += kMlpThreads) S.X[i] = (i < nvalid * kIn) ? p.states[(size_t)s0 * kIn + i] : 0.0f;
+    __syncthreads();
+
+    // ---- forward: actor L1, critic L1, actor L2 (NeuralNetwork.FeedForward, DenseLayer.FeedForward)
+    dense64_forward<kIn, kIn, kIn>(S.X, S.W1, S.b1, S.A1);
+    dense64_forward<kIn, kIn, kIn>(S.X, S.Wc1, S.bc1, S.C1);
+    __syncthreads();
+    dense64_forward<kHid, kPad, kPad>(S.A1, S.W2, S.b2, S.A2);
+    __syncthreads();
+    {  // actor L3 + TanH: thread = (sample, action dim); critic L2: threads 0..63
+      const int s = tid >> 2, k = tid & 3;
+      float sum = 0.0f;
+#pragma unroll 4
+      for (int i = 0; i < kHid; i += 4) {
+        const float4 a = ld4(S.A2 + s * kPad + i), w = ld4(S.W3 + k * kPad + i);
+        sum = fmaf(a.x, w.x, sum);
+        sum = fmaf(a.y, w.y, sum);
+        sum = fmaf(a.z, w.z, sum);
+        sum = fmaf(a.w, w.w, sum);
+      }
+      S.MU[s * kAct + k] = tanhf(sum + S.b3[k]);
+      if (tid < kTile) {
+        float v = 0.0f;
+#pragma unroll 4
+        for (int i = 0; i < kHid; i += 4) {
+          const float4 a = ld4(S.C1 + tid * kPad + i), w = ld4(S.Wc2 + i);
+          v = fmaf(a.x, w.x, v);
+          v = fmaf(a.y, w.y, v);
+          v = fmaf(a.z, w.z, v);
+          v = fmaf(a.w, w.w, v);
+        }
+        S.V[tid] = v + S.bc2[0];
+      }
+    }
+    __syncthreads();
+
+    if (!grad) {
+      const int s = tid >> 2, k = tid & 3;
+      const int gs = s0 + s;
+      if (s < nvalid) {
+        const float mu = S.MU[s * kAct + k];
+        if (p.mean) p.mean[(size_t)gs * kAct + k] = mu;
+        if (p.value && k == 0) p.value[gs] = S.V[s];
+        if (p.mode == kModeSample || p.mode == kModeSamplePhilox) {
+          float u1, u2;
+          if (p.mode == kModeSample) {
+            u1 = p.uniforms[((size_t)gs * kAct + k) * 2];
+            u2 = p.uniforms[((size_t)gs * kAct + k) * 2 + 1];
+          } else {
+            const uint4 r = philox4x32(make_uint4((uint32_t)gs, (uint32_t)k, (uint32_t)p.step, (uint32_t)(p.step >> 32)),
+                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+            u1 = (float)(r.x >> 8) * (1.0f / 16777216.0f);  // [0,1) like (float)Random.NextDouble()
+            u2 = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+          }
+          // NormalDistribution.BoxMullerTransform, NormalDistribution.cs:12-19
+          if (u1 == 0.0f) u1 = 1.0f;
+          const float z = sqrtf(-2.0f * logf(u1)) * sinf(2.0f * 3.14159274f * u2);
+          const float a = mu + (gc.stdv * z);
+          p.out_actions[(size_t)gs * kAct + k] = a;
+          p.out_logp[(size_t)gs * kAct + k] = log_prob(mu, gc.stdv, a, gc.neg_log_std, gc.log_sqrt_2pi);
+        }
+      }
+      continue;
+    }
+
+    // ---- per-sample clipped-surrogate gradient, PPOAgent.cs:232-326 (thread = sample)
+    if (tid < kTile) {
+      const int s = tid, gs = s0 + s;
+      float g[kAct] = {0.f, 0.f, 0.f, 0.f};
+      float gv = 0.0f;
+      if (s < nvalid) {
+        const float adv = p.advantages[gs];
+        bool skip = false;
+#pragma unroll
+        for (int k = 0; k < kAct; k++) {
+          const float mu = S.MU[s * kAct + k];
+          const float a = p.actions[(size_t)gs * kAct + k];
+          const float lp_old = p.old_logp[(size_t)gs * kAct + k];
+          const float lp = log_prob(mu, gc.stdv, a, gc.neg_log_std, gc.log_sqrt_2pi);
+          const float ratio = expf(lp - lp_old);
+          const float clipped = ratio >= gc.upper ? gc.upper : (ratio <= gc.lower ? gc.lower : ratio);  // Matrix.Clip
+          const float cra = clipped * adv, ra = ratio * adv;
+          const float partA = (ra <= cra ? 1.0f : 0.0f) * adv;                              // Matrix.LessThan
+          const float partB = (cra < ra ? 1.0f : 0.0f) * adv;                               // Matrix.LessThanNotEquals
+          const float partC = (ratio >= gc.lower && ratio <= gc.upper) ? 1.0f : 0.0f;       // Matrix.InRange
+          float dclip = (partA + partB * partC) * -1.0f;
+          const float pold = expf(lp_old);
+          if (pold == 0.0f) skip = true;  // HadamardDivision throws -> the sample is skipped (PPOAgent.cs:286-290)
+          dclip = dclip / pold;
+          const float prob = expf(lp);
+          const float dmean = prob * ((a - mu) / gc.variance);
+          g[k] = (dmean * dclip) / p.batch_size;
+        }
+        gv = (2.0f * (S.V[s] - p.returns[gs])) / p.batch_size;
+        if (skip) {
+#pragma unroll
+          for (int k = 0; k < kAct; k++) g[k] = 0.0f;
+          gv = 0.0f;
+          skipped += 1.0f;
+        } else {
+          lossV += gv;
+          lossA += (((g[0] + g[1]) + g[2]) + g[3]) / (float)kAct;  // Matrix.Average
+        }
+      }
+      // TanhLayer.FeedBack: g * (1 - tanh(z)^2), ActivationLayer.cs:18-21,69-72
+#pragma unroll
+      for (int k = 0; k < kAct; k++) {
+        const float mu = S.MU[s * kAct + k];
+        S.G3[s * kAct + k] = g[k] * (1.0f - (mu * mu));
+      }
+      S.GV[s] = gv;
+    }
+    __syncthreads();
+
+    // ---- dL/dz2 = (W3^T g3) * leaky'(z2); dL/dzc1 = (Wc2^T gv) * leaky'(zc1)
+    {
+      const int s = tid >> 2, i0 = (tid & 3) * 16;
+      const float4 g3 = ld4(S.G3 + s * kAct);
+      const float gv = S.GV[s];
+#pragma unroll
+      for (int i = i0; i < i0 + 16; i++) {
+        float sum = 0.0f;
+        sum = fmaf(S.W3[0 * kPad + i], g3.x, sum);
+        sum = fmaf(S.W3[1 * kPad + i], g3.y, sum);
+        sum = fmaf(S.W3[2 * kPad + i], g3.z, sum);
+        sum = fmaf(S.W3[3 * kPad + i], g3.w, sum);
+        S.G2[s * kPad + i] = sum * leaky_grad_from_output(S.A2[s * kPad + i]);
+        S.Gc1[s * kPad + i] = (0.0f + S.Wc2[i] * gv) * leaky_grad_from_output(S.C1[s * kPad + i]);
+      }
+    }
+    __syncthreads();
+
+    // ---- dW3 += g3^T A2 ; dW2 += G2^T A1 ; dL/dz1 = (W2^T G2) * leaky'(z1)
+    {
+      const int k = tid >> 6, i = tid & 63;
+#pragma unroll 8
+      for (int s = 0; s < kTile; s++) accW3 = fmaf(S.G3[s * kAct + k], S.A2[s * kPad + i], accW3);
+    }
+    {
+      const int og = tid >> 4, ig = tid & 15;
+#pragma unroll 4
+      for (int s = 0; s < kTile; s++) {
+        const float4 g4 = ld4(S.G2 + s * kPad + og * 4);
+        const float4 a4 = ld4(S.A1 + s * kPad + ig * 4);
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          accW2[j][0] = fmaf(gg[j], a4.x, accW2[j][0]);
+          accW2[j][1] = fmaf(gg[j], a4.y, accW2[j][1]);
+          accW2[j][2] = fmaf(gg[j], a4.z, accW2[j][2]);
+          accW2[j][3] = fmaf(gg[j], a4.w, accW2[j][3]);
+        }
+      }
+    }
+    {
+      const int ts = tid >> 4, ig = tid & 15;
+      float acc[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int l = 0; l < 4; l++) acc[k][l] = 0.0f;
+#pragma unroll 2
+      for (int o = 0; o < kHid; o += 4) {
+        float4 g4[4], w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) g4[k] = ld4(S.G2 + (ts * 4 + k) * kPad + o);
+#pragma unroll
+        for (int q = 0; q < 4; q++) w4[q] = ld4(S.W2 + (o + q) * kPad + ig * 4);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float gq[4] = {g4[k].x, g4[k].y, g4[k].z, g4[k].w};
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            acc[k][0] = fmaf(w4[q].x, gq[q], acc[k][0]);
+            acc[k][1] = fmaf(w4[q].y, gq[q], acc[k][1]);
+            acc[k][2] = fmaf(w4[q].z, gq[q], acc[k][2]);
+            acc[k][3] = fmaf(w4[q].w, gq[q], acc[k][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int s = ts * 4 + k;
+        const float4 a = ld4(S.A1 + s * kPad + ig * 4);
+        float4 r;
+        r.x = acc[k][0] * leaky_grad_from_output(a.x);
+        r.y = acc[k][1] * leaky_grad_from_output(a.y);
+        r.z = acc[k][2] * leaky_grad_from_output(a.z);
+        r.w = acc[k][3] * leaky_grad_from_output(a.w);
+        *reinterpret_cast<float4*>(S.G1 + s * kPad + ig * 4) = r;
+      }
+    }
+    __syncthreads();
+
+    // ---- dW1 += G1^T X ; dWc1 += Gc1^T X ; biases and the critic head
+    {
+      const int o = tid >> 2, ib = (tid & 3) * 3;
+#pragma unroll 4
+      for (int s = 0; s < kTile; s++) {
+        const float ga = S.G1[s * kPad + o], gcr = S.Gc1[s * kPad + o];
+        const float x0 = S.X[s * kIn + ib], x1 = S.X[s * kIn + ib + 1], x2 = S.X[s * kIn + ib + 2];
+        accW1[0] = fmaf(ga, x0, accW1[0]);
+        accW1[1] = fmaf(ga, x1, accW1[1]);
+        accW1[2] = fmaf(ga, x2, accW1[2]);
+        accWc1[0] = fmaf(gcr, x0, accWc1[0]);
+        accWc1[1] = fmaf(gcr, x1, accWc1[1]);
+        accWc1[2] = fmaf(gcr, x2, accWc1[2]);
+      }
+    }
+    {
+      const int q = tid >> 6, o = tid & 63;  // q: 0 db1, 1 db2, 2 dbc1, 3 dWc2
+      const float* src = (q == 0) ? S.G1 : (q == 1) ? S.G2 : (q == 2) ? S.Gc1 : S.C1;
+#pragma unroll 8
+      for (int s = 0; s < kTile; s++) {
+        const float v = src[s * kPad + o];
+        accS = (q == 3) ? fmaf(S.GV[s], v, accS) : accS + v;
+      }
+      if (tid < kAct + 1) {
+#pragma unroll 8
+        for (int s = 0; s < kTile; s++) accT += (tid < kAct) ? S.G3[s * kAct + tid] : S.GV[s];
+      }
+    }
+  }
+
+  if (!grad) return;
+  // ---- per-CTA partial gradient (flat parameter layout) + loss sums
+  float* out = p.partials + (size_t)blockIdx.x * kGradFloats;
+  {
+    const int og = tid >> 4, ig = tid & 15;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<float4*>(out + kOffW2 + (og * 4 + j) * kHid + ig * 4) =
+          make_float4(accW2[j][0], accW2[j][1], accW2[j][2], accW2[j][3]);
+  }
+  {
+    const int o = tid >> 2, ib = (tid & 3) * 3;
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      out[kOffW1 + o * kIn + ib + l] = accW1[l];
+      out[kOffWc1 + o * kIn + ib + l] = accWc1[l];
+    }
+  }
+  out[kOffW3 + (tid >> 6) * kHid + (tid & 63)] = accW3;
+  {
+    const int q = tid >> 6, o = tid & 63;
+    const int off = (q == 0) ? kOffB1 : (q == 1) ? kOffB2 : (q == 2) ? kOffBc1 : kOffWc2;
+    out[off + o] = accS;
+  }
+  if (tid < kAct) out[kOffB3 + tid] = accT;
+  if (tid == kAct) out[kOffBc2] = accT;
+  // loss sums: only threads < 64 hold non-zero values; fixed-order tree reduction
+  __syncthreads();
+  float* red = S.red;
+  for (int pass = 0; pass < 3; pass++) {
+    red[tid] = (pass == 0) ? lossV : (pass == 1) ? lossA : skipped;
+    __syncthreads();
+    for (int w = kMlpThreads / 2; w > 0; w >>= 1) {
+      if (tid < w) red[tid] += red[tid + w];
+      __syncthreads();
+    }
+    if (tid == 0) out[kTotalParams + pass] = red[0];
+    __syncthreads();
+  }
+  if (tid == 0) out[kGradFloats - 1] = 0.0f;
+}
+
+// grads[i] = sum over CTAs (fixed order) -- this is also NeuralNetwork.Zero(): the buffer is overwritten
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ grads) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kGradFloats) return;
+  float sum = 0.0f;
+  for (int c = 0; c < nparts; c++) sum += partials[(size_t)c * kGradFloats + i];
+  grads[i] = sum;
+}
+
+// DenseLayer.Adam, DenseLayer.cs:125-159 (every product and sum individually rounded, as the Matrix operators do)
+__global__ void adam_kernel(const AdamParams a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kTotalParams) return;
+  const int layer = (i < kOffW2) ? 0 : (i < kOffW3) ? 1 : (i < kActorParams) ? 2 : (i < kOffWc2) ? 3 : 4;
+  const float g = a.grads[i];
+  const float m = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, a.beta1), g), __fmul_rn(a.beta1, a.m[i]));
+  const float v = __fadd_rn(__fmul_rn(a.beta2, a.v[i]), __fmul_rn(__fsub_rn(1.0f, a.beta2), __fmul_rn(g, g)));
+  a.m[i] = m;
+  a.v[i] = v;
+  const float mhat = __fdiv_rn(m, a.corr1[layer]);
+  const float vhat = __fdiv_rn(v, a.corr2[layer]);
+  const float denom = __fadd_rn(__fsqrt_rn(vhat), a.eps);
+  a.params[i] = __fsub_rn(a.params[i], __fmul_rn(a.alpha, __fdiv_rn(mhat, denom)));
+}
+
+// PPOAgent.MonteCarloReturn/MonteCarloAdvantages (:475-498), GeneralizedAdvantageEstimate (:414-444, whose nextGae is
+// never updated in the reference), Normalize (:461-472).  One trajectory: an inherently sequential fp32 recurrence.
+__global__ void returns_kernel(const float* rewards, const float* values, int n, float gamma, float lambda, int use_gae,
+                               int normalize, float norm_eps, float* returns, float* advantages) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (use_gae) {
+    const float next_gae = 0.0f;
+    float next_value = 0.0f;
+    for (int i = n - 1; i >= 0; i--) {
+      const float cur = values[i];
+      const float delta = __fsub_rn(__fadd_rn(rewards[i], __fmul_rn(gamma, next_value)), cur);
+      next_value = cur;
+      const float gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma, lambda), next_gae));
+      advantages[i] = gae;
+      returns[i] = __fadd_rn(gae, values[i]);
+    }
+  } else {
+    float g = 0.0f;
+    for (int i = n - 1; i >= 0; i--) {
+      g = __fadd_rn(rewards[i], __fmul_rn(g, gamma));
+      returns[i] = g;
+    }
+    for (int i = 0; i < n; i++) advantages[i] = __fsub_rn(returns[i], values[i]);
+  }
+  if (normalize && n > 0) {
+    double acc = 0.0;
+    for (int i = 0; i < n; i++) acc += (double)advantages[i];
+    const float mean = (float)(acc / (double)n);
+    double ss = 0.0;
+    for (int i = 0; i < n; i++) {
+      const double d = (double)__fsub_rn(advantages[i], mean);
+      ss += d * d;
+    }
+    const float sd = (float)sqrt(ss / (double)n);
+    const float div = __fadd_rn(sd, norm_eps);
+    for (int i = 0; i < n; i++) advantages[i] = __fdiv_rn(__fsub_rn(advantages[i], mean), div);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+int mlp_grid_for(int n, int sm_count) {
+  const int ntiles = (n + kTile - 1) / kTile;
+  return ntiles < sm_count ? (ntiles > 0 ? ntiles : 1) : sm_count;
+}
+
+cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  GradConsts gc;
+  gc.stdv = expf(p.log_std);                       // PPOAgent.GetStandardDeviations, PPOAgent.cs:367-378
+  gc.neg_log_std = -logf(gc.stdv);                 // NormalDistribution.cs:31
+  gc.log_sqrt_2pi = logf(sqrtf(2.0f * 3.14159274f));
+  gc.upper = 1.0f + p.epsilon;
+  gc.lower = 1.0f - p.epsilon;
+  gc.variance = gc.stdv * gc.stdv;
+  ppo_fused_kernel<<<grid, kMlpThreads, sizeof(MlpSmem), stream>>>(p, gc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_partials(const float* partials, int nparts, float* grads, cudaStream_t stream) {
+  reduce_partials_kernel<<<(kGradFloats + 127) / 128, 128, 0, stream>>>(partials, nparts, grads);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam(const AdamParams& p, cudaStream_t stream) {
+  adam_kernel<<<(kTotalParams + 127) / 128, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_returns(const float* rewards, const float* values, int n, float gamma, float lambda, int use_gae, int normalize,
+                           float norm_eps, float* returns, float* advantages, cudaStream_t stream) {
+  returns_kernel<<<1, 32, 0, stream>>>(rewards, values, n, gamma, lambda, use_gae, normalize, norm_eps, returns, advantages);
+  return cudaGetLastError();
+}
+
+}  // namespace wb

@@ -1,0 +1,78 @@
+// mlp.cuh -- declarations shared by the PPO kernels (mlp.cu) and the policy C ABI (api_policy.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/walker_b200.h"
+
+namespace wb {
+
+// The reference's default topologies (Hyperparameters.cs:91-92): the fused kernels are specialised for them.
+//   actor : 12 -> 64 LeakyReLU -> 64 LeakyReLU -> 4 TanH        (5 252 parameters)
+//   critic: 12 -> 64 LeakyReLU -> 1                             (  897 parameters)
+constexpr int kIn = 12, kHid = 64, kAct = 4;
+// flat parameter layout (DenseLayer.Save order: W[out][in] row-major then b[out], layer after layer)
+constexpr int kOffW1 = 0;                       // [64][12]
+constexpr int kOffB1 = kOffW1 + kHid * kIn;     // 768
+constexpr int kOffW2 = kOffB1 + kHid;           // 832   [64][64]
+constexpr int kOffB2 = kOffW2 + kHid * kHid;    // 4928
+constexpr int kOffW3 = kOffB2 + kHid;           // 4992  [4][64]
+constexpr int kOffB3 = kOffW3 + kAct * kHid;    // 5248
+constexpr int kActorParams = kOffB3 + kAct;     // 5252
+constexpr int kOffWc1 = kActorParams;           // [64][12]
+constexpr int kOffBc1 = kOffWc1 + kHid * kIn;   // +768
+constexpr int kOffWc2 = kOffBc1 + kHid;         // [1][64]
+constexpr int kOffBc2 = kOffWc2 + kHid;
+constexpr int kTotalParams = kOffBc2 + 1;       // 6149
+constexpr int kCriticParams = kTotalParams - kActorParams;  // 897
+// gradient buffer: [6149 grads | sum g_V | sum mean_k g_mu | skipped samples] padded to a float4 multiple
+constexpr int kGradLossV = kTotalParams;
+constexpr int kGradLossA = kTotalParams + 1;
+constexpr int kGradSkipped = kTotalParams + 2;
+constexpr int kGradFloats = 6152;
+
+constexpr int kTile = 64;        // samples per CTA iteration
+constexpr int kMlpThreads = 256;
+
+enum : int { kModeForward = 0, kModeSample = 1, kModeSamplePhilox = 2, kModeGrad = 3 };
+
+struct MlpParams {
+  const float* params;  // [6149] actor | critic
+  int32_t n;
+  int32_t mode;
+  // inputs
+  const float* states;     // [n][12]
+  const float* actions;    // [n][4]   (grad)
+  const float* old_logp;   // [n][4]   (grad)
+  const float* advantages; // [n]      (grad)
+  const float* returns;    // [n]      (grad)
+  const float* uniforms;   // [n][4][2] (sample)
+  uint64_t seed, step;     // (sample, philox)
+  // outputs
+  float* mean;         // [n][4] or null
+  float* value;        // [n] or null
+  float* out_actions;  // [n][4] (sample)
+  float* out_logp;     // [n][4] (sample)
+  float* partials;     // [grid][kGradFloats] (grad)
+  // hyper-parameters
+  float log_std, epsilon, batch_size;
+};
+
+struct AdamParams {
+  float* params;
+  const float* grads;
+  float* m;
+  float* v;
+  float alpha, beta1, beta2, eps;
+  // bias corrections (float)(1 - Math.Pow(beta, t)) per dense layer: actor L1,L2,L3, critic L1,L2
+  float corr1[5], corr2[5];
+};
+
+int mlp_grid_for(int n, int sm_count);
+cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_reduce_partials(const float* partials, int nparts, float* grads, cudaStream_t stream);
+cudaError_t launch_adam(const AdamParams& p, cudaStream_t stream);
+cudaError_t launch_returns(const float* rewards, const float* values, int n, float gamma, float lambda, int use_gae, int normalize,
+                           float norm_eps, float* returns, float* advantages, cudaStream_t stream);
+
+}  // namespace wb

@@ -1,0 +1,55 @@
+// physics.cuh -- shared declarations between the physics kernels (physics.cu) and the C ABI (api.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/walker_b200.h"
+
+namespace wb {
+
+constexpr int kEnvsPerCta = 8;    // environments staged per CTA (one 32-byte sector per SoA row)
+constexpr int kStateFloats = WB_STATE_FLOATS;
+
+struct Material {
+  float inverse_mass, restitution, friction;
+};
+
+// phases of one launch (a fused env-step sets all of the first five)
+enum : int {
+  kPhaseIncSteps = 1,      // Environment.Update: _steps++            (Environment.cs:72)
+  kPhaseTakeActions = 2,   // Matrix.Clip + Walker.TakeActions         (Environment.cs:78)
+  kPhaseStepObjects = 4,   // Environment.StepObjects                  (Environment.cs:126-143)
+  kPhaseObserve = 8,       // Walker.Update + reward/terminal/GetState (Environment.cs:101-121)
+  kPhaseAutoReset = 16,    // Reset + InitialState after a terminal    (Environment.cs:91,157-180)
+  kPhaseObsOnly = 32,      // Walker.GetState only
+  kPhaseResetMasked = 64,  // wb_env_reset: reset envs with mask != 0
+  kPhaseFirstEpisode = 128 // with kPhaseResetMasked: constructor list order (floor last)
+};
+
+struct PhysicsParams {
+  float* state;        // [92][n_pad]
+  int32_t* flags;      // [n_pad]
+  int32_t* steps;      // [n_pad]
+  float* pos;          // [2][n_pad]  Walker._position (Walker.cs:19)
+  const uint8_t* floor_mat;   // [n_pad]
+  const uint8_t* walker_mat;  // [n_pad]
+  const float* actions;       // [n][4]
+  const uint8_t* reset_mask;  // [n] or null
+  float* obs;          // [n][12]
+  float* reward;       // [n]
+  uint8_t* done;       // [n]
+  wb_pair_trace* pair_trace;   // [n][iterations][9] or null
+  wb_joint_trace* joint_trace; // [n][iterations][4] or null
+  int32_t n, n_pad;
+  float dt;            // frame delta (divided by iterations inside, Environment.cs:128)
+  int32_t iterations;
+  int32_t max_timesteps;
+  int32_t phases;
+};
+
+// host-side helpers implemented in physics.cu
+cudaError_t upload_materials(const Material* table, int count);
+cudaError_t upload_scene_constants(const float* init_state92, const float* floor10);
+cudaError_t launch_physics(const PhysicsParams& p, int lanes_per_env, bool trace, cudaStream_t stream);
+
+}  // namespace wb

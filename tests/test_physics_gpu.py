@@ -1,0 +1,147 @@
+"""GPU parity tests proper: the CUDA physics path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bar: contact pairs / axis indices / contact points / state all BIT-EXACT."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MATS = ["Ice", "Wood", "Paper", "Titanium", "Carpet", "Rubber", "Metal", "SuperRubber"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_state_equal(env, ref, what=""):
+    f, iv = env.get_state()
+    rf, riv = ref.get_state()
+    bad = np.argwhere(bits(f) != bits(rf))
+    assert bad.size == 0, f"{what}: {len(bad)} state words differ, first (env,field)={bad[0]} gpu={f[tuple(bad[0])]!r} ref={rf[tuple(bad[0])]!r}"
+    assert np.array_equal(iv, riv), f"{what}: flags/steps differ"
+
+
+def test_initial_state_matches_oracle(gpu, O):
+    env = gpu.EnvBatch(5)
+    ref = O.EnvBatch(5)
+    assert_state_equal(env, ref, "constructor")
+    assert np.array_equal(bits(env.get_obs()), bits(ref.get_obs()))
+
+
+def test_first_step_trace_bit_exact(gpu, O):
+    n = 16
+    env = gpu.EnvBatch(n, floor_materials=[m for m in MATS] * 2)
+    ref = O.EnvBatch(n, floor=MATS * 2)
+    rng = np.random.default_rng(0)
+    for t in range(4):
+        a = rng.uniform(-1.5, 1.5, (n, 4)).astype(np.float32)
+        env.take_actions(a)
+        ref.take_actions(a)
+        pt, jt = env.debug_contacts(gpu.DT_FRAME)
+        rpt, rjt = ref.step_objects(O.DT_FRAME, 50, trace=True)
+        assert np.array_equal(jt.view(np.uint8), rjt.view(np.uint8)), f"joint trace differs at step {t}"
+        for name in pt.dtype.names:
+            assert np.array_equal(pt[name].view(np.uint32), rpt[name].view(np.uint32)), f"pair trace field {name} differs at step {t}"
+        assert_state_equal(env, ref, f"after StepObjects {t}")
+        obs, rew, done = env.observe()
+        robs, rrew, rdone = ref.observe()
+        assert np.array_equal(bits(obs), bits(robs)) and np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone)
+
+
+@pytest.mark.parametrize("n,steps", [(64, 120), (1000, 40)])
+def test_rollout_with_resets_bit_exact(gpu, O, n, steps):
+    """Long enough that walkers fall, terminate and are auto-reset into the floor-first list order."""
+    floors = [MATS[i % 8] for i in range(n)]
+    env = gpu.EnvBatch(n, floor_materials=floors)
+    ref = O.EnvBatch(n, floor=floors)
+    rng = np.random.default_rng(n)
+    ndone = 0
+    for t in range(steps):
+        a = rng.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+        obs, rew, done = env.step(a)
+        robs, rrew, rdone = ref.step(a)
+        assert np.array_equal(done, rdone), f"done differs at step {t}"
+        assert np.array_equal(bits(obs), bits(robs)), f"obs differs at step {t}"
+        assert np.array_equal(bits(rew), bits(rrew)), f"reward differs at step {t}"
+        ndone += int(done.sum())
+    assert_state_equal(env, ref, "end of rollout")
+    if steps >= 100:
+        assert ndone > 0, "rollout never exercised the reset path"
+
+
+def test_set_state_roundtrip_and_identical_start(gpu, O):
+    n = 24
+    ref = O.EnvBatch(n, floor="Wood")
+    rng = np.random.default_rng(3)
+    for _ in range(30):
+        ref.step(rng.uniform(-1, 1, (n, 4)).astype(np.float32))
+    f, iv = ref.get_state()
+    env = gpu.EnvBatch(n, floor_materials="Wood")
+    env.set_state(f, iv)
+    f2, iv2 = env.get_state()
+    assert np.array_equal(bits(f), bits(f2)) and np.array_equal(iv, iv2)
+    a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    obs, rew, done = env.step(a)
+    robs, rrew, rdone = ref.step(a)
+    assert np.array_equal(bits(obs), bits(robs)) and np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone)
+    assert_state_equal(env, ref, "one step from an injected state")
+
+
+def test_contact_stress_all_materials(gpu, O):
+    """cfg5-style: walkers dropped with spin on every floor material; contact pairs/axes bit-exact."""
+    n = 64
+    floors = [MATS[i % 8] for i in range(n)]
+    ref = O.EnvBatch(n, floor=floors)
+    env = gpu.EnvBatch(n, floor_materials=floors)
+    f, iv = ref.get_state()
+    rng = np.random.default_rng(11)
+    f[:, 78:83] = rng.uniform(-5, 5, (n, 5)).astype(np.float32)  # initial angular velocities
+    ref.set_state(f, iv)
+    env.set_state(f, iv)
+    total_contacts = 0
+    for t in range(12):
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        env.take_actions(a)
+        ref.take_actions(a)
+        pt, jt = env.debug_contacts(gpu.DT_FRAME)
+        rpt, rjt = ref.step_objects(O.DT_FRAME, 50, trace=True)
+        for name in pt.dtype.names:
+            assert np.array_equal(pt[name].view(np.uint32), rpt[name].view(np.uint32)), f"{name} differs at step {t}"
+        total_contacts += int(rpt["ncontacts"].sum())
+        env.observe()
+        ref.observe()
+    assert total_contacts > 1000
+    assert_state_equal(env, ref, "stress")
+
+
+def test_user_material_plugin(gpu, O):
+    m = gpu.IMaterial(7.5, 0.55, 0.33).register()
+    assert m.id >= 8
+    env = gpu.EnvBatch(4, floor_materials=m)
+    ref = O.EnvBatch(4, floor=(7.5, 0.55, 0.33))
+    rng = np.random.default_rng(5)
+    for _ in range(25):
+        a = rng.uniform(-1, 1, (4, 4)).astype(np.float32)
+        env.step(a)
+        ref.step(a)
+    assert_state_equal(env, ref, "custom material")
+
+
+def test_ragged_batch_sizes(gpu, O):
+    for n in (1, 7, 9):
+        env = gpu.EnvBatch(n)
+        ref = O.EnvBatch(n)
+        a = np.linspace(-1, 1, n * 4, dtype=np.float32).reshape(n, 4)
+        for _ in range(3):
+            env.step(a)
+            ref.step(a)
+        assert_state_equal(env, ref, f"n={n}")
+
+
+def test_nonfinite_and_out_of_range_actions_are_clipped_like_matrix_clip(gpu, O):
+    n = 8
+    env = gpu.EnvBatch(n)
+    ref = O.EnvBatch(n)
+    a = np.array([[5, -5, 1, -1], [0.999, -0.999, 1e-30, -0.0]] * 4, np.float32)
+    env.step(a)
+    ref.step(a)
+    assert_state_equal(env, ref, "clip")
