@@ -1,0 +1,377 @@
+// api_policy.cu -- C ABI for the PPO policy/value networks (include/walker_b200.h).  Compute is in mlp.cu.
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.h"
+#include "mlp.cuh"
+
+using namespace wb;
+
+struct wb_policy {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  wb_hyperparams hp{};
+  int64_t launches = 0;
+  int32_t iterations[5] = {0, 0, 0, 0, 0};  // DenseLayer._iteration: actor L1..L3, critic L1..L2
+  float* d_params = nullptr;    // [6149] actor | critic
+  float* d_grads = nullptr;     // [kGradFloats]
+  float* d_m = nullptr;         // Adam first moment
+  float* d_v = nullptr;         // Adam second moment
+  float* d_partials = nullptr;  // [sm_count][kGradFloats]
+  // staging for the host-pointer entry points (grown on demand)
+  float* d_stage = nullptr;
+  size_t stage_floats = 0;
+};
+
+static int32_t ensure_stage(wb_policy* p, size_t floats) {
+  if (floats <= p->stage_floats) return WB_OK;
+  if (p->d_stage) cudaFree(p->d_stage);
+  p->d_stage = nullptr;
+  p->stage_floats = 0;
+  WB_CUDA(cudaMalloc(&p->d_stage, floats * sizeof(float)));
+  p->stage_floats = floats;
+  return WB_OK;
+}
+
+static bool is_default_topology(int32_t state_size, int32_t action_size, const int32_t* ak, const int32_t* as, int32_t al,
+                                const int32_t* ck, const int32_t* cs, int32_t cl) {
+  if (state_size != kIn || action_size != kAct || al != 6 || cl != 3) return false;
+  const int32_t want_ak[6] = {WB_DENSE, WB_LEAKYRELU, WB_DENSE, WB_LEAKYRELU, WB_DENSE, WB_TANH};
+  const int32_t want_as[6] = {kHid, 0, kHid, 0, kAct, 0};
+  for (int i = 0; i < 6; i++) {
+    if (ak[i] != want_ak[i]) return false;
+    if (ak[i] == WB_DENSE && as[i] != want_as[i]) return false;
+  }
+  const int32_t want_ck[3] = {WB_DENSE, WB_LEAKYRELU, WB_DENSE};
+  const int32_t want_cs[3] = {kHid, 0, 1};
+  for (int i = 0; i < 3; i++) {
+    if (ck[i] != want_ck[i]) return false;
+    if (ck[i] == WB_DENSE && cs[i] != want_cs[i]) return false;
+  }
+  return true;
+}
+
+static void fill_mlp_common(const wb_policy* p, MlpParams& m, int n, int mode) {
+  m = MlpParams{};
+  m.params = p->d_params;
+  m.n = n;
+  m.mode = mode;
+  m.log_std = p->hp.log_std;
+  m.epsilon = p->hp.epsilon;
+  m.batch_size = (float)p->hp.batch_size;
+}
+
+extern "C" {
+
+int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t* actor_kinds, const int32_t* actor_sizes,
+                         int32_t actor_layers, const int32_t* critic_kinds, const int32_t* critic_sizes, int32_t critic_layers,
+                         const wb_hyperparams* hp, wb_policy** out) {
+  WB_REQUIRE(out, "out is null");
+  *out = nullptr;
+  WB_REQUIRE(actor_kinds && actor_sizes && critic_kinds && critic_sizes, "null layer list");
+  if (!is_default_topology(state_size, action_size, actor_kinds, actor_sizes, actor_layers, critic_kinds, critic_sizes, critic_layers))
+    return fail(WB_ERR_UNSUPPORTED,
+                "the sm_100a kernels are specialised for the reference's default networks "
+                "\"Input |64| (LeakyReLU) |64| (LeakyReLU) |4| (TanH) Output\" / \"Input |64| (LeakyReLU) |1| Output\" "
+                "with 12 inputs (Hyperparameters.cs:91-92)");
+  if (int32_t rc = require_device()) return rc;
+  wb_policy* p = new (std::nothrow) wb_policy();
+  WB_REQUIRE(p, "out of host memory");
+  cudaGetDevice(&p->device);
+  cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
+  if (hp) p->hp = *hp; else wb_hyperparams_default(&p->hp);
+  WB_CUDA(cudaMalloc(&p->d_params, sizeof(float) * kTotalParams));
+  WB_CUDA(cudaMalloc(&p->d_grads, sizeof(float) * kGradFloats));
+  WB_CUDA(cudaMalloc(&p->d_m, sizeof(float) * kTotalParams));
+  WB_CUDA(cudaMalloc(&p->d_v, sizeof(float) * kTotalParams));
+  WB_CUDA(cudaMalloc(&p->d_partials, sizeof(float) * kGradFloats * (size_t)p->sm_count));
+  WB_CUDA(cudaMemset(p->d_params, 0, sizeof(float) * kTotalParams));
+  WB_CUDA(cudaMemset(p->d_grads, 0, sizeof(float) * kGradFloats));
+  WB_CUDA(cudaMemset(p->d_m, 0, sizeof(float) * kTotalParams));
+  WB_CUDA(cudaMemset(p->d_v, 0, sizeof(float) * kTotalParams));
+  *out = p;
+  return WB_OK;
+}
+
+int32_t wb_policy_destroy(wb_policy* p) {
+  if (!p) return WB_OK;
+  cudaFree(p->d_params);
+  cudaFree(p->d_grads);
+  cudaFree(p->d_m);
+  cudaFree(p->d_v);
+  cudaFree(p->d_partials);
+  cudaFree(p->d_stage);
+  delete p;
+  return WB_OK;
+}
+
+int32_t wb_policy_set_stream(wb_policy* p, void* cuda_stream) {
+  WB_REQUIRE(p, "policy is null");
+  p->stream = (cudaStream_t)cuda_stream;
+  return WB_OK;
+}
+
+int32_t wb_policy_sync(wb_policy* p) {
+  WB_REQUIRE(p, "policy is null");
+  WB_CUDA(cudaStreamSynchronize(p->stream));
+  return WB_OK;
+}
+
+int32_t wb_policy_set_hyperparams(wb_policy* p, const wb_hyperparams* hp) {
+  WB_REQUIRE(p && hp, "null argument");
+  p->hp = *hp;
+  return WB_OK;
+}
+
+static int32_t which_range(int32_t which, int* off, int* count) {
+  if (which == 0) {
+    *off = 0;
+    *count = kActorParams;
+  } else if (which == 1) {
+    *off = kActorParams;
+    *count = kCriticParams;
+  } else {
+    return fail(WB_ERR_INVALID, "which must be 0 (actor) or 1 (critic)");
+  }
+  return WB_OK;
+}
+
+int32_t wb_policy_num_params(const wb_policy* p, int32_t which, int32_t* n_out) {
+  WB_REQUIRE(p && n_out, "null argument");
+  int off, count;
+  if (int32_t rc = which_range(which, &off, &count)) return rc;
+  *n_out = count;
+  return WB_OK;
+}
+
+static int32_t copy_range(wb_policy* p, float* dev_base, int32_t which, const float* src_host, float* dst_host) {
+  int off, count;
+  if (int32_t rc = which_range(which, &off, &count)) return rc;
+  if (src_host) WB_CUDA(cudaMemcpyAsync(dev_base + off, src_host, sizeof(float) * count, cudaMemcpyHostToDevice, p->stream));
+  if (dst_host) WB_CUDA(cudaMemcpyAsync(dst_host, dev_base + off, sizeof(float) * count, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaStreamSynchronize(p->stream));
+  return WB_OK;
+}
+
+int32_t wb_policy_set_weights(wb_policy* p, int32_t which, const float* flat_host) {
+  WB_REQUIRE(p && flat_host, "null argument");
+  return copy_range(p, p->d_params, which, flat_host, nullptr);
+}
+int32_t wb_policy_get_weights(wb_policy* p, int32_t which, float* flat_host) {
+  WB_REQUIRE(p && flat_host, "null argument");
+  return copy_range(p, p->d_params, which, nullptr, flat_host);
+}
+int32_t wb_policy_get_grads(wb_policy* p, int32_t which, float* flat_host) {
+  WB_REQUIRE(p && flat_host, "null argument");
+  return copy_range(p, p->d_grads, which, nullptr, flat_host);
+}
+
+int32_t wb_policy_get_adam(wb_policy* p, int32_t which, float* m_host, float* v_host, int32_t* iterations_host) {
+  WB_REQUIRE(p && m_host && v_host && iterations_host, "null argument");
+  if (int32_t rc = copy_range(p, p->d_m, which, nullptr, m_host)) return rc;
+  if (int32_t rc = copy_range(p, p->d_v, which, nullptr, v_host)) return rc;
+  const int first = which == 0 ? 0 : 3, cnt = which == 0 ? 3 : 2;
+  for (int i = 0; i < cnt; i++) iterations_host[i] = p->iterations[first + i];
+  return WB_OK;
+}
+
+int32_t wb_policy_set_adam(wb_policy* p, int32_t which, const float* m_host, const float* v_host, const int32_t* iterations_host) {
+  WB_REQUIRE(p && m_host && v_host && iterations_host, "null argument");
+  if (int32_t rc = copy_range(p, p->d_m, which, m_host, nullptr)) return rc;
+  if (int32_t rc = copy_range(p, p->d_v, which, v_host, nullptr)) return rc;
+  const int first = which == 0 ? 0 : 3, cnt = which == 0 ? 3 : 2;
+  for (int i = 0; i < cnt; i++) p->iterations[first + i] = iterations_host[i];
+  return WB_OK;
+}
+
+// ---- forward / sample
+int32_t wb_policy_forward_dev(wb_policy* p, int32_t n, const float* states_dev, float* mean_dev, float* value_dev) {
+  WB_REQUIRE(p && states_dev, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  MlpParams m;
+  fill_mlp_common(p, m, n, kModeForward);
+  m.states = states_dev;
+  m.mean = mean_dev;
+  m.value = value_dev;
+  WB_CUDA(launch_mlp(m, mlp_grid_for(n, p->sm_count), p->stream));
+  p->launches++;
+  return WB_OK;
+}
+
+int32_t wb_policy_forward(wb_policy* p, int32_t n, const float* states_host, float* mean_host, float* value_host) {
+  WB_REQUIRE(p && states_host, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  const size_t N = (size_t)n;
+  if (int32_t rc = ensure_stage(p, N * (kIn + kAct + 1))) return rc;
+  float* d_states = p->d_stage;
+  float* d_mean = d_states + N * kIn;
+  float* d_value = d_mean + N * kAct;
+  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * kIn, cudaMemcpyHostToDevice, p->stream));
+  if (int32_t rc = wb_policy_forward_dev(p, n, d_states, d_mean, d_value)) return rc;
+  if (mean_host) WB_CUDA(cudaMemcpyAsync(mean_host, d_mean, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
+  if (value_host) WB_CUDA(cudaMemcpyAsync(value_host, d_value, sizeof(float) * N, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaStreamSynchronize(p->stream));
+  return WB_OK;
+}
+
+int32_t wb_policy_sample_dev(wb_policy* p, int32_t n, const float* states_dev, const float* uniforms_dev, float* actions_dev,
+                             float* logp_dev, float* mean_dev) {
+  WB_REQUIRE(p && states_dev && uniforms_dev && actions_dev && logp_dev, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  MlpParams m;
+  fill_mlp_common(p, m, n, kModeSample);
+  m.states = states_dev;
+  m.uniforms = uniforms_dev;
+  m.out_actions = actions_dev;
+  m.out_logp = logp_dev;
+  m.mean = mean_dev;
+  WB_CUDA(launch_mlp(m, mlp_grid_for(n, p->sm_count), p->stream));
+  p->launches++;
+  return WB_OK;
+}
+
+int32_t wb_policy_sample_philox_dev(wb_policy* p, int32_t n, const float* states_dev, uint64_t seed, uint64_t step,
+                                    float* actions_dev, float* logp_dev, float* mean_dev) {
+  WB_REQUIRE(p && states_dev && actions_dev && logp_dev, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  MlpParams m;
+  fill_mlp_common(p, m, n, kModeSamplePhilox);
+  m.states = states_dev;
+  m.seed = seed;
+  m.step = step;
+  m.out_actions = actions_dev;
+  m.out_logp = logp_dev;
+  m.mean = mean_dev;
+  WB_CUDA(launch_mlp(m, mlp_grid_for(n, p->sm_count), p->stream));
+  p->launches++;
+  return WB_OK;
+}
+
+int32_t wb_policy_sample(wb_policy* p, int32_t n, const float* states_host, const float* uniforms_host, float* actions_host,
+                         float* logp_host, float* mean_host) {
+  WB_REQUIRE(p && states_host && uniforms_host && actions_host && logp_host, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  const size_t N = (size_t)n;
+  if (int32_t rc = ensure_stage(p, N * (kIn + kAct * 2 + kAct * 3))) return rc;
+  float* d_states = p->d_stage;
+  float* d_uni = d_states + N * kIn;
+  float* d_act = d_uni + N * kAct * 2;
+  float* d_logp = d_act + N * kAct;
+  float* d_mean = d_logp + N * kAct;
+  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * kIn, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_uni, uniforms_host, sizeof(float) * N * kAct * 2, cudaMemcpyHostToDevice, p->stream));
+  if (int32_t rc = wb_policy_sample_dev(p, n, d_states, d_uni, d_act, d_logp, d_mean)) return rc;
+  WB_CUDA(cudaMemcpyAsync(actions_host, d_act, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaMemcpyAsync(logp_host, d_logp, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
+  if (mean_host) WB_CUDA(cudaMemcpyAsync(mean_host, d_mean, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaStreamSynchronize(p->stream));
+  return WB_OK;
+}
+
+// ---- gradient
+int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
+                        const float* advantages_dev, const float* returns_dev) {
+  WB_REQUIRE(p && states_dev && actions_dev && old_logp_dev && advantages_dev && returns_dev, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  WB_REQUIRE(p->hp.batch_size > 0, "batch_size must be positive");
+  MlpParams m;
+  fill_mlp_common(p, m, n, kModeGrad);
+  m.states = states_dev;
+  m.actions = actions_dev;
+  m.old_logp = old_logp_dev;
+  m.advantages = advantages_dev;
+  m.returns = returns_dev;
+  m.partials = p->d_partials;
+  const int grid = mlp_grid_for(n, p->sm_count);
+  WB_CUDA(launch_mlp(m, grid, p->stream));
+  WB_CUDA(launch_reduce_partials(p->d_partials, grid, p->d_grads, p->stream));
+  p->launches += 2;
+  return WB_OK;
+}
+
+int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
+                    const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host) {
+  WB_REQUIRE(p && states_host && actions_host && old_logp_host && advantages_host && returns_host, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  const size_t N = (size_t)n;
+  if (int32_t rc = ensure_stage(p, N * (kIn + kAct + kAct + 2))) return rc;
+  float* d_states = p->d_stage;
+  float* d_actions = d_states + N * kIn;
+  float* d_logp = d_actions + N * kAct;
+  float* d_adv = d_logp + N * kAct;
+  float* d_ret = d_adv + N;
+  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * kIn, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_actions, actions_host, sizeof(float) * N * kAct, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_logp, old_logp_host, sizeof(float) * N * kAct, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_adv, advantages_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_ret, returns_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
+  if (int32_t rc = wb_ppo_grad_dev(p, n, d_states, d_actions, d_logp, d_adv, d_ret)) return rc;
+  float tail[3] = {0.f, 0.f, 0.f};
+  WB_CUDA(cudaMemcpyAsync(tail, p->d_grads + kGradLossV, sizeof(tail), cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaStreamSynchronize(p->stream));
+  if (losses_host) {
+    losses_host[0] = tail[0];
+    losses_host[1] = tail[1];
+  }
+  if (skipped_host) *skipped_host = (int32_t)tail[2];
+  return WB_OK;
+}
+
+int32_t wb_adam_step(wb_policy* p) {
+  WB_REQUIRE(p, "policy is null");
+  AdamParams a{};
+  a.params = p->d_params;
+  a.grads = p->d_grads;
+  a.m = p->d_m;
+  a.v = p->d_v;
+  a.alpha = p->hp.alpha;
+  a.beta1 = p->hp.beta1;
+  a.beta2 = p->hp.beta2;
+  a.eps = p->hp.adam_epsilon;
+  for (int l = 0; l < 5; l++) {
+    p->iterations[l] += 1;  // DenseLayer.cs:127
+    a.corr1[l] = (float)(1.0 - pow((double)p->hp.beta1, (double)p->iterations[l]));  // :142-145
+    a.corr2[l] = (float)(1.0 - pow((double)p->hp.beta2, (double)p->iterations[l]));
+  }
+  WB_CUDA(launch_adam(a, p->stream));
+  p->launches++;
+  return WB_OK;
+}
+
+int32_t wb_policy_grad_buffer(wb_policy* p, void** dev_ptr_out, int32_t* n_floats_out) {
+  WB_REQUIRE(p && dev_ptr_out && n_floats_out, "null argument");
+  *dev_ptr_out = p->d_grads;
+  *n_floats_out = kGradFloats;
+  return WB_OK;
+}
+
+int32_t wb_policy_launch_count(const wb_policy* p, int64_t* count_out) {
+  WB_REQUIRE(p && count_out, "null argument");
+  *count_out = p->launches;
+  return WB_OK;
+}
+
+int32_t wb_returns_advantages(wb_policy* p, int32_t n, const float* rewards_host, const float* values_host, float* returns_host,
+                              float* advantages_host) {
+  WB_REQUIRE(p && rewards_host && values_host && returns_host && advantages_host, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  const size_t N = (size_t)n;
+  if (int32_t rc = ensure_stage(p, N * 4)) return rc;
+  float* d_r = p->d_stage;
+  float* d_v = d_r + N;
+  float* d_G = d_v + N;
+  float* d_A = d_G + N;
+  WB_CUDA(cudaMemcpyAsync(d_r, rewards_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_v, values_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(launch_returns(d_r, d_v, n, p->hp.gamma, p->hp.lambda, p->hp.use_gae, p->hp.normalize_advantages, p->hp.epsilon, d_G, d_A,
+                         p->stream));
+  p->launches++;
+  WB_CUDA(cudaMemcpyAsync(returns_host, d_G, sizeof(float) * N, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaMemcpyAsync(advantages_host, d_A, sizeof(float) * N, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaStreamSynchronize(p->stream));
+  return WB_OK;
+}
+
+}  // extern "C"

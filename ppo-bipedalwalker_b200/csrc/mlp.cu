@@ -402,7 +402,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) ppo_fused_kernel(const MlpPara
     if (tid == 0) out[kTotalParams + pass] = red[0];
     __syncthreads();
   }
-  if (tid == 0) out[kGradFloats - 1] = 0.0f;
 }
 
 // grads[i] = sum over CTAs (fixed order) -- this is also NeuralNetwork.Zero(): the buffer is overwritten

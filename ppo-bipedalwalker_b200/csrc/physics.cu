@@ -532,20 +532,17 @@ __device__ __forceinline__ void body_step(Ctx& c, int b, float dt, wb_pair_trace
     c.s[kSAngle + b] = ang;
   }
   __syncwarp(c.mask);
-  // ResolveCollisions: candidates in Environment._rigidBodies order, skipping self and associated bodies (Walker.cs:204-208)
-  const int slot = (b == LLL) ? 0 : (b == LLU) ? 2 : (b == BODY) ? 4 : (b == RLL) ? 5 : 7;
-  wb_pair_trace* tr = (TRACE && tr_base) ? tr_base + slot : nullptr;
-  if (b == BODY) {
-    resolve_pair<TRACE>(c, BODY, FLOOR, tr);
-  } else {
-    const int partner = (b == LLL) ? LLU : (b == LLU) ? LLL : (b == RLL) ? RLU : RLL;
-    if (c.flags & WB_FLAG_FLOOR_FIRST) {
-      resolve_pair<TRACE>(c, b, FLOOR, tr);
-      resolve_pair<TRACE>(c, b, partner, tr ? tr + 1 : nullptr);
-    } else {
-      resolve_pair<TRACE>(c, b, partner, tr);
-      resolve_pair<TRACE>(c, b, FLOOR, tr ? tr + 1 : nullptr);
-    }
+  // ResolveCollisions: candidates in Environment._rigidBodies order, skipping self and associated bodies (Walker.cs:204-208):
+  // a leg segment meets the other segment of its own leg and the floor; the Body only the floor.
+  const int slot = (0x75420 >> (4 * b)) & 0xF;             // trace slot base {0,2,4,5,7}
+  const int partner = (0x34F01 >> (4 * b)) & 0xF;          // {LLU, LLL, -, RLU, RLL}
+  const int ncand = (b == BODY) ? 1 : 2;
+  const bool floor_first = (c.flags & WB_FLAG_FLOOR_FIRST) != 0;
+#pragma unroll 1
+  for (int k = 0; k < ncand; k++) {
+    const int other = (b == BODY || (k == 0) == floor_first) ? FLOOR : partner;
+    wb_pair_trace* tr = (TRACE && tr_base) ? tr_base + slot + k : nullptr;
+    resolve_pair<TRACE>(c, b, other, tr);
   }
 }
 
@@ -649,17 +646,15 @@ __global__ void __launch_bounds__(kEnvsPerCta * 16) physics_step_kernel(const Ph
           if (p.joint_trace) jt = p.joint_trace + ((size_t)env * p.iterations + it) * 4;
           if (p.pair_trace) pt = p.pair_trace + ((size_t)env * p.iterations + it) * WB_PAIR_SLOTS;  // all 9 slots are written every substep
         }
-        // joints in creation order (Walker.cs:182-187)
-        joint_step<TRACE>(c, BODY, 1, LLU, 4, jt);
-        joint_step<TRACE>(c, BODY, 1, RLU, 4, jt ? jt + 1 : nullptr);
-        joint_step<TRACE>(c, LLU, 2, LLL, 3, jt ? jt + 2 : nullptr);
-        joint_step<TRACE>(c, RLU, 2, RLL, 3, jt ? jt + 3 : nullptr);
+        // joints in creation order (Walker.cs:182-187): (Body v1, LLU v4) (Body v1, RLU v4) (LLU v2, LLL v3) (RLU v2, RLL v3)
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+          const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
+          joint_step<TRACE>(c, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, jt ? jt + k : nullptr);
+        }
         // bodies in list order; the static floor's Update is a no-op (a = v = 0, returns before rotation/collisions)
-        body_step<TRACE>(c, LLL, dt, pt);
-        body_step<TRACE>(c, LLU, dt, pt);
-        body_step<TRACE>(c, BODY, dt, pt);
-        body_step<TRACE>(c, RLL, dt, pt);
-        body_step<TRACE>(c, RLU, dt, pt);
+#pragma unroll 1
+        for (int b = 0; b < 5; b++) body_step<TRACE>(c, b, dt, pt);
       }
     }
 

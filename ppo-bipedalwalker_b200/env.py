@@ -94,7 +94,7 @@ class EnvBatch:
             self.set_stream(stream)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # `lib` is None during interpreter shutdown
             lib().wb_env_destroy(self._h)
             self._h = None
 
