@@ -189,7 +189,7 @@ int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const 
 /* NeuralNetwork.Optimise -> DenseLayer.Adam on both networks (NeuralNetwork.cs:85-91, DenseLayer.cs:125-159) */
 int32_t wb_adam_step(wb_policy* p);
 /* device address + length of the contiguous gradient buffer [actor | critic | 2 loss sums | skipped] for the
- * caller's all-reduce (NCCL over NVLink through torch.distributed, or wb_comm below) */
+ * caller's all-reduce (one NCCL all-reduce(sum) over NVLink per minibatch, issued by the host process) */
 int32_t wb_policy_grad_buffer(wb_policy* p, void** dev_ptr_out, int32_t* n_floats_out);
 int32_t wb_policy_launch_count(const wb_policy* p, int64_t* count_out);
 

@@ -5,7 +5,5 @@ from ._lib import Hyperparams, WalkerB200Error, declared_symbols, lib  # noqa: F
 from .env import (DT_FRAME, MATERIALS, Carpet, EnvBatch, Environment, Ice, IMaterial, Metal, Paper, Rubber,  # noqa: F401
                   SuperRubber, Titanium, Walker, Wood, default_hyperparams, init, JOINT_TRACE_DTYPE, PAIR_TRACE_DTYPE)
 
-try:  # the policy half is optional only while the library is being brought up
-    from .ppo import *  # noqa: F401,F403
-except ImportError:  # pragma: no cover
-    pass
+from . import dist  # noqa: F401
+from .ppo import *  # noqa: F401,F403

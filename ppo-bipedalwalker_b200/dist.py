@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing: one process per GPU, environments block-sharded with no data-path collective; the only
+exchange is the all-reduce(sum) of the PPO gradient buffer (6 149 fp32 + 3 scalars) per minibatch, NCCL over
+NVLink through torch.distributed (gloo on CPU for the tests).  SURVEY.md section 8e."""
+from __future__ import annotations
+
+import os
+
+
+def world():
+    """(rank, local_rank, world_size) from the torchrun environment (1 process = 1 GPU)."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard_range(n_total: int, rank: int, world_size: int):
+    """Contiguous block of environments / samples owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(n_total, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class DeviceBuffer:
+    """Zero-copy view of a raw device pointer for torch (`torch.as_tensor(DeviceBuffer(...), device='cuda')`)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def grad_tensor(agent):
+    """The policy handle's gradient buffer as a torch CUDA tensor (no copy)."""
+    import torch
+    ptr, n = agent.grad_buffer()
+    return torch.as_tensor(DeviceBuffer(ptr, n), device=f"cuda:{torch.cuda.current_device()}")
+
+
+def allreduce_sum_(tensor):
+    """In-place sum over ranks; a no-op without an initialised process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+def train_minibatch_sharded(agent, states, actions, logp, advantages, returns, grad_view=None):
+    """One data-parallel PPO minibatch: local gradient over this rank's shard (already divided by the GLOBAL
+    batch size hp.batch_size), all-reduce(sum), identical Adam on every rank (weights stay bit-identical)."""
+    out = agent.Gradients(states, actions, logp, advantages, returns)
+    if grad_view is None:
+        grad_view = grad_tensor(agent)
+    allreduce_sum_(grad_view)
+    agent.Optimise()
+    return out

@@ -145,3 +145,35 @@ def test_nonfinite_and_out_of_range_actions_are_clipped_like_matrix_clip(gpu, O)
     env.step(a)
     ref.step(a)
     assert_state_equal(env, ref, "clip")
+
+
+def test_committed_golden_rollout(gpu):
+    """The CUDA path against the committed fixture (tests/golden/physics_rollout.npz): no oracle at run time."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "physics_rollout.npz"))
+    env = gpu.EnvBatch(8, floor_materials=[str(x) for x in g["floors"]])
+    for t in range(g["actions"].shape[0]):
+        obs, rew, done = env.step(g["actions"][t])
+        f, iv = env.get_state()
+        assert np.array_equal(bits(f), bits(g["states"][t])), f"state differs from the golden fixture at step {t}"
+        assert np.array_equal(iv, g["ints"][t]) and np.array_equal(bits(obs), bits(g["obs"][t]))
+        assert np.array_equal(bits(rew), bits(g["reward"][t])) and np.array_equal(done, g["done"][t])
+
+
+def test_full_size_properties_4096_walkers(gpu):
+    """BASELINE configs[1] size: size-independent properties -- identical envs stay identical in lockstep, walkers never
+    tunnel through the floor, every record stays finite, episodes terminate and reset."""
+    n = 4096
+    env = gpu.EnvBatch(n, floor_materials="Wood")
+    rng = np.random.default_rng(0)
+    base = rng.uniform(-1, 1, (60, 8, 4)).astype(np.float32)
+    total_done = 0
+    for t in range(60):
+        a = np.tile(base[t], (n // 8, 1))  # env i and env i+8 receive identical actions
+        obs, rew, done = env.step(a)
+        total_done += int(done.sum())
+        assert np.array_equal(obs[:8].view(np.uint32), obs[8:16].view(np.uint32))
+        assert np.array_equal(obs.reshape(n // 8, 8, 12)[0].view(np.uint32), obs.reshape(n // 8, 8, 12)[-1].view(np.uint32))
+    f, iv = env.get_state()
+    assert np.isfinite(f).all() and f[:, 1:58:2].max() < 915
+    assert total_done > 0 and (iv[:, 1] <= 60).all()
