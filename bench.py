@@ -62,7 +62,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -100,7 +100,7 @@ def make_actions(n, steps, rank):
     return rng.uniform(-1.0, 1.0, (steps, n, 4)).astype(np.float32)
 
 
-def cpu_baseline(O, budget_s=10.0, max_steps=200, nthreads=0):
+def cpu_baseline(O, budget_s=12.0, max_steps=4000, nthreads=0):
     """The oracle port on the host cores: the same workload, a bounded sample (~budget_s of CPU work)."""
     n = N_ENVS_PER_GPU
     env = O.EnvBatch(n, floor="Wood")
