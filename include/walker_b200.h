@@ -143,6 +143,10 @@ int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out);
 /* which kernel variant wb_env_step uses: lanes per environment (16 or 32); 0 = library default */
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env);
 
+/* test hook: the rotation coefficients (float)Math.Cos((double)r), (float)Math.Sin((double)r) of Matrix.CreateRotationZ as used by
+ * Skeleton.Rotate (Skeleton.cs:93). mode 0: production path, 1: forced double-double path, 2: forced device sincos path */
+int32_t wb_debug_rotz(int32_t n, const float* radians_host, int32_t mode, float* cos_host, float* sin_host);
+
 /* ---- policy: Walker/PPO/PPOAgent.cs, Network/, Matrix.cs ---- */
 /* layer kinds of the network DSL (PPOAgent.ParseLayers, PPOAgent.cs:96-143) */
 enum { WB_DENSE = 0, WB_RELU = 1, WB_LEAKYRELU = 2, WB_TANH = 3 };

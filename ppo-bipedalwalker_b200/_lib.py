@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         "wb_env_step_dev": (C.c_int32, [vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
         "wb_env_launch_count": (C.c_int32, [vp, i64p]),
         "wb_env_set_variant": (C.c_int32, [vp, C.c_int32]),
+        "wb_debug_rotz": (C.c_int32, [C.c_int32, vp, C.c_int32, vp, vp]),
         "wb_policy_create": (C.c_int32, [C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, hpp, C.POINTER(vp)]),
         "wb_policy_destroy": (C.c_int32, [vp]),
         "wb_policy_set_stream": (C.c_int32, [vp, vp]),

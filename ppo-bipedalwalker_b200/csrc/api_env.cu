@@ -448,4 +448,20 @@ int32_t wb_env_step_dev(wb_env_batch* env, const float* actions_dev, float delta
   return launch(env, step_phases(auto_reset), delta_time, actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, nullptr);
 }
 
+int32_t wb_debug_rotz(int32_t n, const float* radians_host, int32_t mode, float* cos_host, float* sin_host) {
+  WB_REQUIRE(n > 0 && radians_host && cos_host && sin_host, "bad argument");
+  if (int32_t rc = require_device()) return rc;
+  float *d_in = nullptr, *d_c = nullptr, *d_s = nullptr;
+  WB_CUDA(cudaMalloc(&d_in, sizeof(float) * 3 * (size_t)n));
+  d_c = d_in + n;
+  d_s = d_c + n;
+  cudaError_t e = cudaMemcpy(d_in, radians_host, sizeof(float) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_rotz_debug(d_in, n, mode, d_c, d_s, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(cos_host, d_c, sizeof(float) * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(sin_host, d_s, sizeof(float) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  if (e != cudaSuccess) return fail(WB_ERR_CUDA, "wb_debug_rotz: %s", cudaGetErrorString(e));
+  return WB_OK;
+}
+
 }  // extern "C"

@@ -78,10 +78,76 @@ __device__ __forceinline__ float net_min(float a, float b) {
   return signbit(a) ? a : b;
 }
 
-// Matrix.CreateRotationZ (MonoGame): (float)Math.Cos((double)r), (float)Math.Sin((double)r)
+// ---- (float)Math.Cos((double)r), (float)Math.Sin((double)r) for Matrix.CreateRotationZ (MonoGame)
+// double-double helpers for the (rare) slow path
+struct dd { double hi, lo; };
+__device__ __forceinline__ dd dd_two_sum(double a, double b) { double s = a + b, bb = s - a; return {s, (a - (s - bb)) + (b - bb)}; }
+__device__ __forceinline__ dd dd_mul(dd a, dd b) {
+  double p = a.hi * b.hi, e = fma(a.hi, b.hi, -p) + (a.hi * b.lo + a.lo * b.hi);
+  double s = p + e; return {s, e - (s - p)};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+  dd s = dd_two_sum(a.hi, b.hi); double e = s.lo + (a.lo + b.lo); double h = s.hi + e; return {h, e - (h - s.hi)};
+}
+__device__ __forceinline__ dd dd_div_int(dd a, double n) {  // a / n for a small integer n
+  double q = a.hi / n; double r = fma(-q, n, a.hi) + a.lo; double q2 = r / n; double h = q + q2; return {h, q2 - (h - q)};
+}
+// correctly rounded float of a double-double: only an exact float-midpoint in hi needs lo to break the tie
+__device__ __forceinline__ float dd_to_float(dd v) {
+  long long b = __double_as_longlong(v.hi);
+  if (((unsigned)b & 0x1FFFFFFFu) == 0x10000000u && v.lo != 0.0) b += ((v.lo > 0.0) == (v.hi > 0.0)) ? 1 : -1;
+  return (float)__longlong_as_double(b);
+}
+// sin/cos of |x| < 2^-5 in double-double (Taylor series, ~100 bits): only used when the fast result is within one double
+// ulp of a float rounding boundary, so that the float we return is the correctly rounded one.
+__device__ __noinline__ void sincos_dd_small(double x, float& c, float& s) {
+  const dd X = {x, 0.0};
+  const dd X2 = dd_mul(X, X);
+  dd term = X, sum = X;  // sin: x - x^3/3! + x^5/5! - ...
+#pragma unroll 1
+  for (int k = 1; k <= 9; k++) {
+    term = dd_div_int(dd_mul(term, X2), -(double)((2 * k) * (2 * k + 1)));
+    sum = dd_add(sum, term);
+  }
+  s = dd_to_float(sum);
+  term = {1.0, 0.0};
+  sum = {1.0, 0.0};      // cos: 1 - x^2/2! + x^4/4! - ...
+#pragma unroll 1
+  for (int k = 1; k <= 9; k++) {
+    term = dd_div_int(dd_mul(term, X2), -(double)((2 * k - 1) * (2 * k)));
+    sum = dd_add(sum, term);
+  }
+  c = dd_to_float(sum);
+}
+
+// true when the double r is within one ulp of the midpoint between two adjacent floats (its rounding to float is then
+// not decided by a <=0.5-ulp-accurate double)
+__device__ __forceinline__ bool float_rounding_ambiguous(double r) {
+  const unsigned lo = (unsigned)__double2loint(r) & 0x1FFFFFFFu;  // the 29 mantissa bits a float drops
+  return (lo - 0x0FFFFFFFu) <= 2u;
+}
+
 __device__ __forceinline__ void rotz(float radians, float& c, float& s) {
+  const double x = (double)radians;
+  if (fabsf(radians) < 0.03125f) {
+    // per-substep angles are tiny (omega * 3.3e-4): Taylor polynomials in double, truncation error < 2^-70 relative,
+    // total error ~0.5 ulp -- at least as accurate as a libm call, so the float rounding matches a correctly rounded libm
+    const double x2 = x * x;
+    double ps = fma(x2, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
+    ps = fma(x2, ps, 8.3333333333333332e-03);                               // 1/5!
+    ps = fma(x2, ps, -1.6666666666666666e-01);                              // -1/3!
+    const double sd = fma(x * x2, ps, x);
+    double pc = fma(x2, 2.4801587301587302e-05, -1.3888888888888889e-03);   // 1/8!, -1/6!
+    pc = fma(x2, pc, 4.1666666666666664e-02);                               // 1/4!
+    pc = fma(x2, pc, -0.5);
+    const double cd = fma(x2, pc, 1.0);
+    c = (float)cd;
+    s = (float)sd;
+    if (float_rounding_ambiguous(cd) || (float_rounding_ambiguous(sd) && fabsf(radians) > 1e-30f)) sincos_dd_small(x, c, s);
+    return;
+  }
   double sd, cd;
-  sincos((double)radians, &sd, &cd);
+  sincos(x, &sd, &cd);
   c = (float)cd;
   s = (float)sd;
 }
@@ -156,6 +222,21 @@ __device__ __forceinline__ void apply_impulses(BodyDyn& A, BodyDyn& B, float2 n,
   B.v = velB;
   A.w = wA;
   B.w = wB;
+}
+
+// min over the 16 lanes of the group / over the 8 lanes of my half (butterflies stay inside the group)
+__device__ __forceinline__ unsigned group_umin16(const Ctx& c, unsigned v) {
+  v = min(v, __shfl_xor_sync(c.mask, v, 1));
+  v = min(v, __shfl_xor_sync(c.mask, v, 2));
+  v = min(v, __shfl_xor_sync(c.mask, v, 4));
+  v = min(v, __shfl_xor_sync(c.mask, v, 8));
+  return v;
+}
+__device__ __forceinline__ unsigned half_umin8(const Ctx& c, unsigned v) {
+  v = min(v, __shfl_xor_sync(c.mask, v, 1));
+  v = min(v, __shfl_xor_sync(c.mask, v, 2));
+  v = min(v, __shfl_xor_sync(c.mask, v, 4));
+  return v;
 }
 
 // lane 0 stores body X's (v, w), lane 8 body Y's; the floor is never written (inverse mass/inertia 0)
@@ -292,7 +373,7 @@ __device__ __forceinline__ bool sat(const Ctx& c, int A, int B, float2& normal, 
   // every eligible depth is > 0 here, so the uint order of the bit patterns is the float order;
   // "tempDepth >= depth -> continue" keeps the FIRST minimal axis: lowest lane among the minima.
   const unsigned key = elig ? __float_as_uint(temp) : 0xFFFFFFFFu;
-  const unsigned best = __reduce_min_sync(c.mask, key);
+  const unsigned best = group_umin16(c, key);
   const unsigned winners = (__ballot_sync(c.mask, elig && key == best) >> c.gshift) & 0xFFFFu;
   if (winners) {
     const int w = __ffs(winners) - 1;
@@ -312,24 +393,28 @@ struct Face {
   float2 a, b, max;
 };
 
-// GetSignificantVertex + GetSignificantFace, ContactPoints.cs:79-113
-__device__ __forceinline__ Face significant_face(const Ctx& c, int P, float2 nrm) {
+// GetSignificantVertex + GetSignificantFace, ContactPoints.cs:79-113, for BOTH polygons at once:
+// lanes 0..7 work on polygon A with `normal` (reference face), lanes 8..15 on polygon B with -normal (incident face).
+// Lane i projects vertex i; the first strictly-smallest projection wins (min over the half on an order-preserving key,
+// lowest lane among equals), exactly as the sequential "if (!(projection < minimumDistance)) continue" scan.
+__device__ __forceinline__ void significant_faces(const Ctx& c, int A, int B, float2 normal, Face& fa, Face& fb) {
+  const bool hi = c.gl >= 8;
+  const int i = c.gl & 7;
+  const int P = hi ? B : A;
   const int n = nverts(P);
-  float2 sv = mk2(0.0f, 0.0f);
-  int k = -1;
-  float md = FLT_MAX;
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    if (j < n) {
-      float2 v = lds2(c.s, svert(P, j));
-      float pr = vdot(v, nrm);
-      if (pr < md) {
-        md = pr;
-        k = j;
-        sv = v;
-      }
+  const float2 nrm = hi ? vneg(normal) : normal;
+  unsigned key = 0xFFFFFFFFu;
+  if (i < n) {
+    const float pr = vdot(lds2(c.s, svert(P, i)), nrm);
+    if (pr < FLT_MAX) {  // NaN and values >= float.MaxValue never replace the initial minimum
+      const unsigned b = __float_as_uint(fadd(pr, 0.0f));  // -0 -> +0: equal values get equal keys
+      key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
     }
   }
+  const unsigned best = half_umin8(c, key);
+  const unsigned winners = (__ballot_sync(c.mask, key == best) >> (c.gshift + (hi ? 8 : 0))) & 0xFFu;
+  const int k = (best == 0xFFFFFFFFu) ? -1 : (__ffs(winners) - 1);
+  const float2 sv = (k >= 0) ? lds2(c.s, svert(P, k)) : mk2(0.0f, 0.0f);
   int ka = k + 1;
   if (ka >= n) ka -= n;
   int kb = k - 1;
@@ -338,16 +423,16 @@ __device__ __forceinline__ Face significant_face(const Ctx& c, int P, float2 nrm
   const float2 pb = lds2(c.s, svert(P, kb));
   const float2 after = vnormalize(vsub(sv, pa));
   const float2 before = vnormalize(vsub(sv, pb));
-  Face f;
-  if (vdot(nrm, before) >= vdot(nrm, after)) {
-    f.a = sv;
-    f.b = pb;
-  } else {
-    f.a = pa;
-    f.b = sv;
-  }
-  f.max = sv;
-  return f;
+  const bool use_before = vdot(nrm, before) >= vdot(nrm, after);
+  const float2 a = use_before ? sv : pa;
+  const float2 b = use_before ? pb : sv;
+  const int la = c.gshift, lb = c.gshift + 8;
+  fa.a = mk2(__shfl_sync(c.mask, a.x, la), __shfl_sync(c.mask, a.y, la));
+  fa.b = mk2(__shfl_sync(c.mask, b.x, la), __shfl_sync(c.mask, b.y, la));
+  fa.max = mk2(__shfl_sync(c.mask, sv.x, la), __shfl_sync(c.mask, sv.y, la));
+  fb.a = mk2(__shfl_sync(c.mask, a.x, lb), __shfl_sync(c.mask, a.y, lb));
+  fb.b = mk2(__shfl_sync(c.mask, b.x, lb), __shfl_sync(c.mask, b.y, lb));
+  fb.max = mk2(__shfl_sync(c.mask, sv.x, lb), __shfl_sync(c.mask, sv.y, lb));
 }
 
 // ClipVectors, ContactPoints.cs:56-76: appends up to 3 points; only the first two are ever used
@@ -378,9 +463,9 @@ __device__ __forceinline__ bool veq(float2 a, float2 b) { return a.x == b.x && a
 
 // GetContactPoints, ContactPoints.cs:13-53
 __device__ __forceinline__ int contact_points(const Ctx& c, int A, int B, float2 normal, float2& c0, float2& c1) {
-  Face ref = significant_face(c, A, normal);
+  Face ref, inc;
+  significant_faces(c, A, B, normal, ref, inc);
   float2 rf = vsub(ref.b, ref.a);
-  Face inc = significant_face(c, B, vneg(normal));
   const float2 ifv = vsub(inc.b, inc.a);
   if (fabsf(vdot(rf, normal)) > fabsf(vdot(ifv, normal))) {
     Face t = ref;
@@ -482,13 +567,17 @@ __device__ __forceinline__ void resolve_pair(Ctx& c, int A, int B, wb_pair_trace
         const float e = (B == FLOOR) ? c.e_wf : c.e_ww;
         const float mu = (B == FLOOR) ? c.mu_wf : c.mu_ww;
         const float2 contact = (ncp == 2) ? vhalf(vadd(c0, c1)) : c0;
-        float2 rA, rB, rAf, rBf;
-        float j, jf;
-        calculate_impulse(X, Y, contact, fadd(1.0f, e), normal, rA, rB, j);
+        // both impulses come from the PRE-impulse velocities (Impulses.cs:23-24): lanes 0..7 evaluate the normal one,
+        // lanes 8..15 the tangential one, then both are applied in the reference's order (:26-27)
+        const bool hi = c.gl >= 8;
         const float2 tangent = mk2(-normal.y, normal.x);
-        calculate_impulse(X, Y, contact, mu, tangent, rAf, rBf, jf);
+        float2 rA, rB;
+        float jmine;
+        calculate_impulse(X, Y, contact, hi ? mu : fadd(1.0f, e), hi ? tangent : normal, rA, rB, jmine);
+        const float j = __shfl_sync(c.mask, jmine, c.gshift);
+        const float jf = __shfl_sync(c.mask, jmine, c.gshift + 8);
         apply_impulses(X, Y, normal, j, rA, rB);
-        apply_impulses(X, Y, tangent, jf, rAf, rBf);
+        apply_impulses(X, Y, tangent, jf, rA, rB);
         store_dyn_pair(c, A, X, B, Y);
       }
     }
@@ -570,8 +659,12 @@ __device__ __forceinline__ void write_initial_record(const Ctx& c) {
   __syncwarp(c.mask);
 }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(kEnvsPerCta * 16) physics_step_kernel(const PhysicsParams p) {
+// LANES = 16: two environments share a warp (fewest warp-instructions per env; best when the GPU is full).
+// LANES = 32: one environment per warp, lanes 0..15 work: the group mask is the compile-time constant 0xFFFF, so every
+//             warp-level primitive is a plain WARPSYNC/SHFL/VOTE (a per-group mask costs MATCH+REDUX+VOTE+branch each),
+//             there is no cross-environment divergence, and twice as many warps hide latency when N is small.
+template <int LANES, bool TRACE>
+__global__ void __launch_bounds__(kEnvsPerCta * LANES, LANES == 32 ? 4 : 1) physics_step_kernel(const PhysicsParams p) {
   __shared__ __align__(16) float smem[kEnvsPerCta * kSStride];
   const int tid = threadIdx.x;
   const int env0 = blockIdx.x * kEnvsPerCta;
@@ -586,17 +679,22 @@ __global__ void __launch_bounds__(kEnvsPerCta * 16) physics_step_kernel(const Ph
     smem[(h * 4 + 2) * kSStride + so] = v.z;
     smem[(h * 4 + 3) * kSStride + so] = v.w;
   }
-  const int g = tid >> 4;  // group = env inside the CTA
+  const int g = tid / LANES;  // group = env inside the CTA
   const int env = env0 + g;
   Ctx c;
   c.s = smem + g * kSStride;
-  c.gl = tid & 15;
-  c.gshift = (tid & 16);
-  c.mask = 0xFFFFu << c.gshift;
+  c.gl = tid % LANES;
+  if (LANES == 16) {
+    c.gshift = (tid & 16);
+    c.mask = 0xFFFFu << c.gshift;
+  } else {
+    c.gshift = 0;
+    c.mask = 0x0000FFFFu;
+  }
   if (c.gl < 10) c.s[(c.gl < 8 ? svert(FLOOR, 0) : kSCen + FLOOR * 2 - 8) + c.gl] = c_floor[c.gl];
   __syncthreads();
 
-  const bool live = env < p.n;
+  const bool live = env < p.n && c.gl < 16;
   if (live) {
     c.flags = p.flags[env];
     int steps = p.steps[env];
@@ -713,7 +811,32 @@ __global__ void __launch_bounds__(kEnvsPerCta * 16) physics_step_kernel(const Ph
   }
 }
 
+// test hook: evaluates the rotation coefficients for an array of angles (mode 0: production path, 1: force the
+// double-double slow path, 2: force the libm-style sincos path)
+__global__ void rotz_debug_kernel(const float* radians, int n, int mode, float* c_out, float* s_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float c, s;
+  if (mode == 1) {
+    sincos_dd_small((double)radians[i], c, s);
+  } else if (mode == 2) {
+    double sd, cd;
+    sincos((double)radians[i], &sd, &cd);
+    c = (float)cd;
+    s = (float)sd;
+  } else {
+    rotz(radians[i], c, s);
+  }
+  c_out[i] = c;
+  s_out[i] = s;
+}
+
 // ---------------------------------------------------------------- host side
+cudaError_t launch_rotz_debug(const float* radians, int n, int mode, float* c_out, float* s_out, cudaStream_t stream) {
+  rotz_debug_kernel<<<(n + 255) / 256, 256, 0, stream>>>(radians, n, mode, c_out, s_out);
+  return cudaGetLastError();
+}
+
 cudaError_t upload_materials(const Material* table, int count) {
   return cudaMemcpyToSymbol(c_materials, table, sizeof(Material) * count);
 }
@@ -725,13 +848,18 @@ cudaError_t upload_scene_constants(const float* init_state92, const float* floor
 }
 
 cudaError_t launch_physics(const PhysicsParams& p, int lanes_per_env, bool trace, cudaStream_t stream) {
-  (void)lanes_per_env;
   const int grid = p.n_pad / kEnvsPerCta;
-  const int block = kEnvsPerCta * 16;
-  if (trace)
-    physics_step_kernel<true><<<grid, block, 0, stream>>>(p);
-  else
-    physics_step_kernel<false><<<grid, block, 0, stream>>>(p);
+  if (lanes_per_env == 32) {
+    if (trace)
+      physics_step_kernel<32, true><<<grid, kEnvsPerCta * 32, 0, stream>>>(p);
+    else
+      physics_step_kernel<32, false><<<grid, kEnvsPerCta * 32, 0, stream>>>(p);
+  } else {
+    if (trace)
+      physics_step_kernel<16, true><<<grid, kEnvsPerCta * 16, 0, stream>>>(p);
+    else
+      physics_step_kernel<16, false><<<grid, kEnvsPerCta * 16, 0, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

@@ -50,6 +50,7 @@ struct PhysicsParams {
 // host-side helpers implemented in physics.cu
 cudaError_t upload_materials(const Material* table, int count);
 cudaError_t upload_scene_constants(const float* init_state92, const float* floor10);
+cudaError_t launch_rotz_debug(const float* radians, int n, int mode, float* c_out, float* s_out, cudaStream_t stream);
 cudaError_t launch_physics(const PhysicsParams& p, int lanes_per_env, bool trace, cudaStream_t stream);
 
 }  // namespace wb

@@ -177,3 +177,57 @@ def test_full_size_properties_4096_walkers(gpu):
     f, iv = env.get_state()
     assert np.isfinite(f).all() and f[:, 1:58:2].max() < 915
     assert total_done > 0 and (iv[:, 1] <= 60).all()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_rotation_coefficients_match_libm_rounded_to_float(gpu, O, mode):
+    """(float)cos((double)theta), (float)sin((double)theta): the polynomial fast path, the forced double-double path and
+    the device sincos path against the host libm (what .NET's Math.Cos/Sin call) on 2M angles incl. per-substep-sized ones."""
+    import ctypes as C
+    from ppo_bipedalwalker_b200._lib import check, lib, ptr
+    rng = np.random.default_rng(mode)
+    small = (rng.uniform(-1, 1, 1_500_000) * 10.0 ** rng.uniform(-7, -1.6, 1_500_000)).astype(np.float32)
+    edge = np.array([0.0, -0.0, 1e-38, -1e-38, 1e-45, 0.03124999, -0.03124999, 3.3333397e-4, 1e-20], np.float32)
+    big = rng.uniform(-0.03125, 0.03125, 500_000).astype(np.float32) if mode == 1 else rng.uniform(-7, 7, 500_000).astype(np.float32)
+    ang = np.concatenate([small, edge, big])
+    if mode == 1:
+        ang = ang[np.abs(ang) < 0.03125]
+    c = np.empty_like(ang)
+    s = np.empty_like(ang)
+    check(lib().wb_debug_rotz(ang.size, ptr(ang), mode, ptr(c), ptr(s)))
+    rc = np.cos(ang.astype(np.float64)).astype(np.float32)
+    rs = np.sin(ang.astype(np.float64)).astype(np.float32)
+    bad_c = int((c.view(np.uint32) != rc.view(np.uint32)).sum())
+    bad_s = int(((s.view(np.uint32) != rs.view(np.uint32)) & ~((s == 0) & (rs == 0))).sum())
+    if mode == 2:
+        assert bad_c + bad_s <= 2   # two independent <=1-2 ulp libms: agreement after float rounding is statistical
+    else:
+        assert bad_c == 0 and bad_s == 0
+
+
+@pytest.mark.parametrize("lanes", [16, 32])
+def test_kernel_variants_bit_exact(gpu, O, lanes):
+    """Both thread mappings (two envs per warp / one env per warp) against the oracle, traces included."""
+    n = 40
+    floors = [MATS[i % 8] for i in range(n)]
+    env = gpu.EnvBatch(n, floor_materials=floors)
+    env.set_variant(lanes)
+    ref = O.EnvBatch(n, floor=floors)
+    rng = np.random.default_rng(lanes)
+    for t in range(70):
+        a = rng.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+        if t % 10 == 0:
+            env.take_actions(a)
+            ref.take_actions(a)
+            pt, jt = env.debug_contacts(gpu.DT_FRAME)
+            rpt, rjt = ref.step_objects(O.DT_FRAME, 50, trace=True)
+            assert np.array_equal(jt.view(np.uint8), rjt.view(np.uint8))
+            for name in pt.dtype.names:
+                assert np.array_equal(pt[name].view(np.uint32), rpt[name].view(np.uint32)), f"{name} differs at step {t}"
+            env.observe()
+            ref.observe()
+        else:
+            obs, rew, done = env.step(a)
+            robs, rrew, rdone = ref.step(a)
+            assert np.array_equal(bits(obs), bits(robs)) and np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone)
+    assert_state_equal(env, ref, f"lanes={lanes}")
