@@ -197,6 +197,11 @@ int32_t wb_adam_step(wb_policy* p);
 int32_t wb_policy_grad_buffer(wb_policy* p, void** dev_ptr_out, int32_t* n_floats_out);
 int32_t wb_policy_launch_count(const wb_policy* p, int64_t* count_out);
 
+/* test hook for the tcgen05 building block: one CTA computes D[M x N] = A[M x K] * B[N x K]^T on the tensor cores
+ * (kind::tf32; passes = 1 plain TF32, 3 = 3xTF32 split).  a/b_mn_major choose how the operand tile is read (K-major / MN-major). */
+int32_t wb_debug_tc_gemm(int32_t M, int32_t N, int32_t K, int32_t a_mn_major, int32_t b_mn_major, int32_t passes, const float* A_host,
+                         const float* B_host, float* D_host);
+
 /* rollout -> update glue (PPOAgent.cs:414-498), one trajectory of length n on the device */
 int32_t wb_returns_advantages(wb_policy* p, int32_t n, const float* rewards_host, const float* values_host, float* returns_host,
                               float* advantages_host);

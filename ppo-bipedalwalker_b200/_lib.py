@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
         "wb_policy_grad_buffer": (C.c_int32, [vp, C.POINTER(vp), ip]),
         "wb_policy_launch_count": (C.c_int32, [vp, i64p]),
         "wb_returns_advantages": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp]),
+        "wb_debug_tc_gemm": (C.c_int32, [C.c_int32] * 6 + [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares

@@ -374,4 +374,27 @@ int32_t wb_returns_advantages(wb_policy* p, int32_t n, const float* rewards_host
   return WB_OK;
 }
 
+int32_t wb_debug_tc_gemm(int32_t M, int32_t N, int32_t K, int32_t a_mn_major, int32_t b_mn_major, int32_t passes, const float* A_host,
+                         const float* B_host, float* D_host) {
+  WB_REQUIRE(A_host && B_host && D_host, "null argument");
+  WB_REQUIRE((M == 64 || M == 128) && N >= 8 && N <= 128 && N % 8 == 0 && K >= 8 && K % 8 == 0, "unsupported test shape");
+  WB_REQUIRE(sizeof(float) * 2 * ((size_t)M * K + (size_t)N * K) <= 200 * 1024, "test shape exceeds shared memory");
+  if (int32_t rc = require_device()) return rc;
+  float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+  WB_CUDA(cudaMalloc(&dA, sizeof(float) * M * K));
+  WB_CUDA(cudaMalloc(&dB, sizeof(float) * N * K));
+  WB_CUDA(cudaMalloc(&dD, sizeof(float) * M * N));
+  cudaError_t e = cudaMemcpy(dA, A_host, sizeof(float) * M * K, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dB, B_host, sizeof(float) * N * K, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(dD, 0, sizeof(float) * M * N);
+  if (e == cudaSuccess) e = launch_tc_gemm_test(dA, dB, dD, M, N, K, a_mn_major, b_mn_major, passes, nullptr);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(D_host, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost);
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dD);
+  if (e != cudaSuccess) return fail(WB_ERR_CUDA, "wb_debug_tc_gemm: %s", cudaGetErrorString(e));
+  return WB_OK;
+}
+
 }  // extern "C"
