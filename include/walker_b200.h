@@ -159,6 +159,8 @@ int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t*
 int32_t wb_policy_destroy(wb_policy* p);
 int32_t wb_policy_set_stream(wb_policy* p, void* cuda_stream);
 int32_t wb_policy_sync(wb_policy* p);
+/* kernel variant of the MLP path: 0 = tcgen05 tensor-core kernel with 3xTF32 operands (default), 1 = fp32 CUDA-core kernel */
+int32_t wb_policy_set_variant(wb_policy* p, int32_t variant);
 int32_t wb_policy_set_hyperparams(wb_policy* p, const wb_hyperparams* hp);
 /* flat parameter vectors, per dense layer W[out][in] row-major then b[out] (DenseLayer.Save, DenseLayer.cs:73-79). which: 0 actor, 1 critic */
 int32_t wb_policy_num_params(const wb_policy* p, int32_t which, int32_t* n_out);

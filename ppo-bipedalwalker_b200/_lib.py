@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         "wb_policy_destroy": (C.c_int32, [vp]),
         "wb_policy_set_stream": (C.c_int32, [vp, vp]),
         "wb_policy_sync": (C.c_int32, [vp]),
+        "wb_policy_set_variant": (C.c_int32, [vp, C.c_int32]),
         "wb_policy_set_hyperparams": (C.c_int32, [vp, hpp]),
         "wb_policy_num_params": (C.c_int32, [vp, C.c_int32, ip]),
         "wb_policy_set_weights": (C.c_int32, [vp, C.c_int32, vp]),

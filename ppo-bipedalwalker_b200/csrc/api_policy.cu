@@ -14,6 +14,7 @@ struct wb_policy {
   cudaStream_t stream = nullptr;
   wb_hyperparams hp{};
   int64_t launches = 0;
+  int variant = 0;  // 0: tcgen05 tensor-core kernel (default), 1: fp32 CUDA-core kernel
   int32_t iterations[5] = {0, 0, 0, 0, 0};  // DenseLayer._iteration: actor L1..L3, critic L1..L2
   float* d_params = nullptr;    // [6149] actor | critic
   float* d_grads = nullptr;     // [kGradFloats]
@@ -52,6 +53,12 @@ static bool is_default_topology(int32_t state_size, int32_t action_size, const i
   }
   return true;
 }
+
+static cudaError_t run_mlp(wb_policy* p, const MlpParams& m) {
+  if (p->variant == 1) return launch_mlp(m, mlp_grid_for(m.n, p->sm_count), p->stream);
+  return launch_mlp_tc(m, tc_grid_for(m.n, p->sm_count), p->stream);
+}
+static int grid_of(const wb_policy* p, int n) { return p->variant == 1 ? mlp_grid_for(n, p->sm_count) : tc_grid_for(n, p->sm_count); }
 
 static void fill_mlp_common(const wb_policy* p, MlpParams& m, int n, int mode) {
   m = MlpParams{};
@@ -110,6 +117,13 @@ int32_t wb_policy_destroy(wb_policy* p) {
 int32_t wb_policy_set_stream(wb_policy* p, void* cuda_stream) {
   WB_REQUIRE(p, "policy is null");
   p->stream = (cudaStream_t)cuda_stream;
+  return WB_OK;
+}
+
+int32_t wb_policy_set_variant(wb_policy* p, int32_t variant) {
+  WB_REQUIRE(p, "policy is null");
+  WB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (tensor-core) or 1 (CUDA-core)");
+  p->variant = variant;
   return WB_OK;
 }
 
@@ -195,7 +209,7 @@ int32_t wb_policy_forward_dev(wb_policy* p, int32_t n, const float* states_dev, 
   m.states = states_dev;
   m.mean = mean_dev;
   m.value = value_dev;
-  WB_CUDA(launch_mlp(m, mlp_grid_for(n, p->sm_count), p->stream));
+  WB_CUDA(run_mlp(p, m));
   p->launches++;
   return WB_OK;
 }
@@ -227,7 +241,7 @@ int32_t wb_policy_sample_dev(wb_policy* p, int32_t n, const float* states_dev, c
   m.out_actions = actions_dev;
   m.out_logp = logp_dev;
   m.mean = mean_dev;
-  WB_CUDA(launch_mlp(m, mlp_grid_for(n, p->sm_count), p->stream));
+  WB_CUDA(run_mlp(p, m));
   p->launches++;
   return WB_OK;
 }
@@ -244,7 +258,7 @@ int32_t wb_policy_sample_philox_dev(wb_policy* p, int32_t n, const float* states
   m.out_actions = actions_dev;
   m.out_logp = logp_dev;
   m.mean = mean_dev;
-  WB_CUDA(launch_mlp(m, mlp_grid_for(n, p->sm_count), p->stream));
+  WB_CUDA(run_mlp(p, m));
   p->launches++;
   return WB_OK;
 }
@@ -284,8 +298,8 @@ int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const 
   m.advantages = advantages_dev;
   m.returns = returns_dev;
   m.partials = p->d_partials;
-  const int grid = mlp_grid_for(n, p->sm_count);
-  WB_CUDA(launch_mlp(m, grid, p->stream));
+  const int grid = grid_of(p, n);
+  WB_CUDA(run_mlp(p, m));
   WB_CUDA(launch_reduce_partials(p->d_partials, grid, p->d_grads, p->stream));
   p->launches += 2;
   return WB_OK;

@@ -75,6 +75,8 @@ cudaError_t launch_adam(const AdamParams& p, cudaStream_t stream);
 cudaError_t launch_returns(const float* rewards, const float* values, int n, float gamma, float lambda, int use_gae, int normalize,
                            float norm_eps, float* returns, float* advantages, cudaStream_t stream);
 
+int tc_grid_for(int n, int sm_count);
+cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M, int N, int K, int a_mn, int b_mn, int passes,
                                 cudaStream_t stream);
 

@@ -143,4 +143,521 @@ cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M,
   return cudaGetLastError();
 }
 
+
+
+// ============================================================================================================
+// ppo_tc_kernel: the fused PPO pipeline with every GEMM on the 5th-gen tensor cores.
+//
+// Replaces PPOAgent.Train(Batch)'s per-sample Matrix pipeline (PPOAgent.cs:218-346; DenseLayer.FeedForward/FeedBack,
+// DenseLayer.cs:82-120) for the default networks.  Per 64-sample tile (thread = sample for the 64 "sample threads",
+// lanes 0..15 of each warp = the TMEM lanes an M=64 accumulator occupies):
+//   F1   [64 x 16] x [16 x 128]   X|1  ->  A1pre | C1pre   (biases ride in the ones column)          tcgen05, K-major
+//   F2   [64 x 64] x [64 x 64]    A1   ->  A2pre                                                    tcgen05, K-major
+//        L3 (64->4, tanh), critic head (64->1), clipped-surrogate gradient: registers, reference summation order
+//   dW3' [128 x 64s] x [64s x 8]  [C1|A2]^T x [g3|gv]      -> dWc2, dW3 (accumulated in TMEM over all tiles)  MN-major
+//   B2   [64 x 64] x [64 x 64]    G2 x W2 -> dL/dA1                                                 K-major A, MN-major B
+//   dW2  [64 x 64s] x [64s x 64]  G2^T x A1                (accumulated)                             MN-major
+//   dB2  [64 x 64s] x [64s x 16]  G2^T x [X|1]             (column 12 = db2, accumulated)            MN-major
+//   dW1  [128 x 64s] x [64s x 16] [G1|Gc1]^T x [X|1]       -> dW1, db1, dWc1, dbc1 (accumulated)     MN-major
+// All operand tiles use the dual-use B32 layout above, fp32 accuracy via 3xTF32 (hi*hi + lo*hi + hi*lo).
+// ============================================================================================================
+constexpr int kS = 64;           // samples per tile
+constexpr int kBlk = kS * 32;    // floats in one 32-feature block of a 64-row tile (8 KB)
+constexpr int kTcThreads = 160;   // warps 0..3: one TMEM sub-partition each (epilogue / per-sample math); warp 4: MMA issuer
+
+struct __align__(1024) TcSmem {
+  float xt_hi[kBlk], xt_lo[kBlk];            // [X(12) | 1 | 0 0 0] per sample
+  float act_hi[6 * kBlk], act_lo[6 * kBlk];  // blocks 0-1: A1 -> G1, 2-3: C1 -> Gc1, 4-5: A2 -> G2
+  float g3v_hi[kBlk], g3v_lo[kBlk];          // [g3(4) | gv | 0 0 0] per sample
+  float w2_hi[2 * kBlk], w2_lo[2 * kBlk];    // rows = o (64), features = i (64)
+  float w1_hi[128 * 32], w1_lo[128 * 32];    // rows = [W1 o | Wc1 o] (128), features = [i(12) | bias | 0 0 0]
+  float w3[kAct * kHid], wc2[kHid], b2[kHid], b3[kAct], bc2[4];
+  float red[256];
+  uint64_t mbar;
+  uint32_t tmem_slot;
+};
+
+// TMEM column map (fp32 columns)
+constexpr uint32_t kColF1 = 0, kColF2 = 128, kColB2 = 192, kColDW2 = 256, kColDB2 = 320, kColDW1 = 336, kColDW3 = 352;
+constexpr uint32_t kTmemCols = 512;
+
+enum : int { kKMajor = 0, kMnMajor = 1 };
+
+// one 3xTF32 MMA chain: D[tmem] (+)= A * B over `ksteps` k-steps of 8
+//   K-major tile  (rows x features): k-step advances 32 B inside a 128-B row; every 4 k-steps the next 32-feature block (rows*128 B)
+//   MN-major tile (features x rows): k-step advances 8 rows = 1024 B; LBO = rows*128 B between 32-feature blocks
+__device__ __forceinline__ void issue_chain(uint32_t tmem_d, int M, int N, const float* a_hi, const float* a_lo, int a_major, int a_rows,
+                                            const float* b_hi, const float* b_lo, int b_major, int b_rows, int ksteps, bool accumulate) {
+  const uint32_t idesc = tc::make_idesc_tf32(M, N, a_major, b_major);
+  const uint32_t a_lbo = a_major == kMnMajor ? (uint32_t)a_rows * 128u : 0u;
+  const uint32_t b_lbo = b_major == kMnMajor ? (uint32_t)b_rows * 128u : 0u;
+  bool acc = accumulate;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; pass++) {
+    const uint32_t a_base = tc::smem_u32(pass == 1 ? a_lo : a_hi);
+    const uint32_t b_base = tc::smem_u32(pass == 2 ? b_lo : b_hi);
+#pragma unroll 1
+    for (int ks = 0; ks < ksteps; ks++) {
+      const uint32_t a_off = a_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * a_rows * 128u + (uint32_t)(ks & 3) * 32u;
+      const uint32_t b_off = b_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * b_rows * 128u + (uint32_t)(ks & 3) * 32u;
+      const uint64_t da = tc::make_smem_desc(a_base + a_off, a_lbo, 512u) | kLayoutB32;
+      const uint64_t db = tc::make_smem_desc(b_base + b_off, b_lbo, 512u) | kLayoutB32;
+      tc::mma_tf32(tmem_d, da, db, idesc, acc);
+      acc = true;
+    }
+  }
+}
+
+// store 8 consecutive features [f0, f0+8) of sample s into a dual-use tile (hi and lo parts)
+__device__ __forceinline__ void store_unit(float* hi_tile, float* lo_tile, int s, int f0, const float* v) {
+  float h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) tc::split_tf32(v[j], h[j], l[j]);
+  const int off = tile_off_b32(s, f0, kS);
+  *reinterpret_cast<float4*>(hi_tile + off) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(hi_tile + off + 4) = make_float4(h[4], h[5], h[6], h[7]);
+  *reinterpret_cast<float4*>(lo_tile + off) = make_float4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<float4*>(lo_tile + off + 4) = make_float4(l[4], l[5], l[6], l[7]);
+}
+
+__device__ __forceinline__ float tc_leaky(float v) { return fmaxf(0.2f * v, v); }
+
+__device__ __forceinline__ float tc_log_prob(float mean, float stdv, float action, float neg_log_std, float log_sqrt_2pi) {
+  float fraction = (action - mean) / stdv;
+  fraction *= fraction;
+  fraction /= 2.0f;
+  return neg_log_std - log_sqrt_2pi - fraction;
+}
+
+__device__ __forceinline__ uint4 tc_philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+struct TcConsts {
+  float stdv, neg_log_std, log_sqrt_2pi, upper, lower, variance;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p, const TcConsts gc) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool epi = warp < 4;                       // epilogue warps own TMEM lanes 32w..32w+31
+  const bool is_sample = epi && lane < 16;         // lanes 32w..32w+15 hold rows 16w..16w+15 of an M=64 accumulator
+  const int s_loc = (warp & 3) * 16 + (lane & 15);
+  const bool issuer = tid == 128;                  // lane 0 of the dedicated issuer warp: tcgen05.mma / commit
+  const bool grad = p.mode == kModeGrad;
+
+  if (warp == 0) tc::tmem_alloc(&S.tmem_slot, kTmemCols);
+  if (tid == 0) {
+    tc::mbar_init(&S.mbar, 1);
+    tc::mbar_fence_init();
+  }
+  // ---- weights -> dual-use tiles (once per CTA)
+  for (int i = tid; i < 2 * kBlk; i += kTcThreads) {
+    S.w2_hi[i] = 0.f;
+    S.w2_lo[i] = 0.f;
+  }
+  for (int i = tid; i < 128 * 32; i += kTcThreads) {
+    S.w1_hi[i] = 0.f;
+    S.w1_lo[i] = 0.f;
+  }
+  for (int i = tid; i < kBlk; i += kTcThreads) {
+    S.xt_hi[i] = 0.f;
+    S.xt_lo[i] = 0.f;
+    S.g3v_hi[i] = 0.f;
+    S.g3v_lo[i] = 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < kHid * kHid; i += kTcThreads) {
+    const int o = i >> 6, in = i & 63;
+    float h, l;
+    tc::split_tf32(p.params[kOffW2 + i], h, l);
+    const int off = tile_off_b32(o, in, kHid);
+    S.w2_hi[off] = h;
+    S.w2_lo[off] = l;
+  }
+  for (int i = tid; i < 128 * 13; i += kTcThreads) {
+    const int r = i / 13, f = i % 13;  // f < 12: weight, f == 12: bias
+    const float w = (r < kHid) ? (f < 12 ? p.params[kOffW1 + r * kIn + f] : p.params[kOffB1 + r])
+                               : (f < 12 ? p.params[kOffWc1 + (r - kHid) * kIn + f] : p.params[kOffBc1 + (r - kHid)]);
+    float h, l;
+    tc::split_tf32(w, h, l);
+    const int off = tile_off_b32(r, f, 128);
+    S.w1_hi[off] = h;
+    S.w1_lo[off] = l;
+  }
+  for (int i = tid; i < kAct * kHid; i += kTcThreads) S.w3[i] = p.params[kOffW3 + i];
+  if (tid < kHid) {
+    S.wc2[tid] = p.params[kOffWc2 + tid];
+    S.b2[tid] = p.params[kOffB2 + tid];
+  }
+  if (tid < kAct) S.b3[tid] = p.params[kOffB3 + tid];
+  if (tid == 0) S.bc2[0] = p.params[kOffBc2];
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = S.tmem_slot;
+  const uint32_t tmem_warp = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t phase = 0;
+
+  float lossV = 0.f, lossA = 0.f, skipped = 0.f;
+  float db3_acc[kAct] = {0.f, 0.f, 0.f, 0.f}, dbc2_acc = 0.f;
+  bool any_tile = false;
+
+  const int ntiles = (p.n + kS - 1) / kS;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int s0 = tile * kS;
+    const int nvalid = min(kS, p.n - s0);
+    const int gs = s0 + s_loc;
+    const bool valid = is_sample && s_loc < nvalid;
+
+    // ---- P0: stage [X | 1] (coalesced global read, 16 features per sample; ones column = bias input)
+    for (int i = tid; i < kS * 16; i += kTcThreads) {
+      const int s = i >> 4, f = i & 15;
+      float v = 0.f;
+      if (s < nvalid) v = (f < kIn) ? p.states[(size_t)(s0 + s) * kIn + f] : (f == kIn ? 1.0f : 0.f);
+      float h, l;
+      tc::split_tf32(v, h, l);
+      const int off = tile_off_b32(s, f, kS);
+      S.xt_hi[off] = h;
+      S.xt_lo[off] = l;
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+
+    // ---- P1: F1 = [X|1] x [W1|b1 ; Wc1|bc1]^T  -> 128 columns
+    if (issuer) {
+      issue_chain(tmem + kColF1, 64, 128, S.xt_hi, S.xt_lo, kKMajor, kS, S.w1_hi, S.w1_lo, kKMajor, 128, 2, false);
+      tc::mma_commit(&S.mbar);
+    }
+    if (epi) tc::mbar_wait(&S.mbar, phase);
+    phase ^= 1;
+    __syncwarp();
+    tc::fence_after_thread_sync();
+
+    // ---- P2: A1 = leaky(.), C1 = leaky(.), V = Wc2 . C1 + bc2 (left-to-right), derivative masks
+    unsigned long long maskA1 = 0, maskC1 = 0, maskA2 = 0;
+    float value = 0.f;
+    if (epi)
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 16) {
+      float v[16];
+      tc::tmem_ld_x16(tmem_warp + kColF1 + c, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        v[j] = tc_leaky(v[j]);
+        const unsigned long long neg = v[j] < 0.0f ? 1ull : 0ull;
+        if (c < 64) {
+          maskA1 |= neg << (c + j);
+        } else {
+          maskC1 |= neg << (c - 64 + j);
+          value = fmaf(v[j], S.wc2[c - 64 + j], value);
+        }
+      }
+      if (is_sample) {
+        store_unit(S.act_hi, S.act_lo, s_loc, c, v);
+        store_unit(S.act_hi, S.act_lo, s_loc, c + 8, v + 8);
+      }
+    }
+    value += S.bc2[0];
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+
+    // ---- P3: F2 = A1 x W2^T
+    if (issuer) {
+      issue_chain(tmem + kColF2, 64, 64, S.act_hi, S.act_lo, kKMajor, kS, S.w2_hi, S.w2_lo, kKMajor, kHid, 8, false);
+      tc::mma_commit(&S.mbar);
+    }
+    if (epi) tc::mbar_wait(&S.mbar, phase);
+    phase ^= 1;
+    __syncwarp();
+    tc::fence_after_thread_sync();
+
+    // ---- P4: A2 = leaky(. + b2); mu = tanh(W3 . A2 + b3) accumulated left to right
+    float mu[kAct] = {0.f, 0.f, 0.f, 0.f};
+    if (epi)
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 16) {
+      float v[16];
+      tc::tmem_ld_x16(tmem_warp + kColF2 + c, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        v[j] = tc_leaky(v[j] + S.b2[c + j]);
+        maskA2 |= (v[j] < 0.0f ? 1ull : 0ull) << (c + j);
+#pragma unroll
+        for (int k = 0; k < kAct; k++) mu[k] = fmaf(v[j], S.w3[k * kHid + c + j], mu[k]);
+      }
+      if (is_sample && grad) {
+        store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c, v);
+        store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c + 8, v + 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kAct; k++) mu[k] = tanhf(mu[k] + S.b3[k]);
+
+    if (!grad) {
+      if (valid) {
+        if (p.value) p.value[gs] = value;
+#pragma unroll
+        for (int k = 0; k < kAct; k++) {
+          if (p.mean) p.mean[(size_t)gs * kAct + k] = mu[k];
+          if (p.mode == kModeSample || p.mode == kModeSamplePhilox) {
+            float u1, u2;
+            if (p.mode == kModeSample) {
+              u1 = p.uniforms[((size_t)gs * kAct + k) * 2];
+              u2 = p.uniforms[((size_t)gs * kAct + k) * 2 + 1];
+            } else {
+              const uint4 r = tc_philox4x32(make_uint4((uint32_t)gs, (uint32_t)k, (uint32_t)p.step, (uint32_t)(p.step >> 32)),
+                                            make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+              u1 = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+              u2 = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+            }
+            if (u1 == 0.0f) u1 = 1.0f;  // NormalDistribution.BoxMullerTransform, NormalDistribution.cs:12-19
+            const float z = sqrtf(-2.0f * logf(u1)) * sinf(2.0f * 3.14159274f * u2);
+            const float a = mu[k] + (gc.stdv * z);
+            p.out_actions[(size_t)gs * kAct + k] = a;
+            p.out_logp[(size_t)gs * kAct + k] = tc_log_prob(mu[k], gc.stdv, a, gc.neg_log_std, gc.log_sqrt_2pi);
+          }
+        }
+      }
+      __syncthreads();  // every warp is done with this tile's TMEM columns and smem tiles
+      continue;
+    }
+
+    // ---- per-sample clipped-surrogate gradient (PPOAgent.cs:232-326), tanh backward
+    float g3[kAct] = {0.f, 0.f, 0.f, 0.f}, gv = 0.f;
+    if (valid) {
+      const float adv = p.advantages[gs];
+      bool skip = false;
+#pragma unroll
+      for (int k = 0; k < kAct; k++) {
+        const float a = p.actions[(size_t)gs * kAct + k];
+        const float lp_old = p.old_logp[(size_t)gs * kAct + k];
+        const float lp = tc_log_prob(mu[k], gc.stdv, a, gc.neg_log_std, gc.log_sqrt_2pi);
+        const float ratio = expf(lp - lp_old);
+        const float clipped = ratio >= gc.upper ? gc.upper : (ratio <= gc.lower ? gc.lower : ratio);
+        const float cra = clipped * adv, ra = ratio * adv;
+        const float partA = (ra <= cra ? 1.0f : 0.0f) * adv;
+        const float partB = (cra < ra ? 1.0f : 0.0f) * adv;
+        const float partC = (ratio >= gc.lower && ratio <= gc.upper) ? 1.0f : 0.0f;
+        float dclip = (partA + partB * partC) * -1.0f;
+        const float pold = expf(lp_old);
+        if (pold == 0.0f) skip = true;
+        dclip = dclip / pold;
+        const float dmean = expf(lp) * ((a - mu[k]) / gc.variance);
+        g3[k] = (dmean * dclip) / p.batch_size;
+      }
+      gv = (2.0f * (value - p.returns[gs])) / p.batch_size;
+      if (skip) {
+#pragma unroll
+        for (int k = 0; k < kAct; k++) g3[k] = 0.f;
+        gv = 0.f;
+        skipped += 1.0f;
+      } else {
+        lossV += gv;
+        lossA += (((g3[0] + g3[1]) + g3[2]) + g3[3]) / (float)kAct;
+      }
+#pragma unroll
+      for (int k = 0; k < kAct; k++) {
+        g3[k] = g3[k] * (1.0f - (mu[k] * mu[k]));  // TanhLayer.FeedBack
+        db3_acc[k] += g3[k];
+      }
+      dbc2_acc += gv;
+    }
+    if (is_sample) {
+      const float u[8] = {g3[0], g3[1], g3[2], g3[3], gv, 0.f, 0.f, 0.f};
+      store_unit(S.g3v_hi, S.g3v_lo, s_loc, 0, u);
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+
+    // ---- P5: [C1|A2]^T x [g3|gv]  (accumulates dWc2 and dW3 over all tiles)
+    if (issuer) {
+      issue_chain(tmem + kColDW3, 128, 8, S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, kMnMajor, kS, S.g3v_hi, S.g3v_lo, kMnMajor, kS, 8, any_tile);
+      tc::mma_commit(&S.mbar);
+    }
+    // dL/dz2 = (W3^T g3) * leaky'(z2) in registers while the tensor core runs (sum over k from 0, Matrix.Multiply order)
+    if (epi) tc::mbar_wait(&S.mbar, phase);
+    phase ^= 1;
+    __syncwarp();
+    tc::fence_after_thread_sync();
+    if (epi)
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int o = c + j;
+        float sum = 0.f;
+        sum = fmaf(S.w3[0 * kHid + o], g3[0], sum);
+        sum = fmaf(S.w3[1 * kHid + o], g3[1], sum);
+        sum = fmaf(S.w3[2 * kHid + o], g3[2], sum);
+        sum = fmaf(S.w3[3 * kHid + o], g3[3], sum);
+        v[j] = sum * (((maskA2 >> o) & 1ull) ? 0.2f : 1.0f);
+      }
+      if (is_sample) store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c, v);  // G2 overwrites A2
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+
+    // ---- P6: dL/dA1 = G2 x W2 ; dW2 += G2^T x A1 ; dB2 += G2^T x [X|1]
+    if (issuer) {
+      issue_chain(tmem + kColB2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kKMajor, kS, S.w2_hi, S.w2_lo, kMnMajor, kHid, 8, false);
+      issue_chain(tmem + kColDW2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.act_hi, S.act_lo, kMnMajor, kS, 8, any_tile);
+      issue_chain(tmem + kColDB2, 64, 16, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, any_tile);
+      tc::mma_commit(&S.mbar);
+    }
+    if (epi) tc::mbar_wait(&S.mbar, phase);
+    phase ^= 1;
+    __syncwarp();
+    tc::fence_after_thread_sync();
+
+    // ---- P7: G1 = dL/dA1 * leaky'(z1) ; Gc1 = (Wc2^T gv) * leaky'(zc1)  -> overwrite A1 | C1
+    if (epi)
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 16) {
+      float v[16], w[16];
+      tc::tmem_ld_x16(tmem_warp + kColB2 + c, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int i = c + j;
+        v[j] = v[j] * (((maskA1 >> i) & 1ull) ? 0.2f : 1.0f);
+        w[j] = (0.0f + S.wc2[i] * gv) * (((maskC1 >> i) & 1ull) ? 0.2f : 1.0f);
+      }
+      if (is_sample) {
+        store_unit(S.act_hi, S.act_lo, s_loc, c, v);
+        store_unit(S.act_hi, S.act_lo, s_loc, c + 8, v + 8);
+        store_unit(S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, s_loc, c, w);
+        store_unit(S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, s_loc, c + 8, w + 8);
+      }
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+
+    // ---- P8: [G1|Gc1]^T x [X|1]  (accumulates dW1, db1, dWc1, dbc1)
+    if (issuer) {
+      issue_chain(tmem + kColDW1, 128, 16, S.act_hi, S.act_lo, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, any_tile);
+      tc::mma_commit(&S.mbar);
+    }
+    if (epi) tc::mbar_wait(&S.mbar, phase);  // the next tile overwrites XT and ACT
+    phase ^= 1;
+    __syncwarp();
+    tc::fence_after_thread_sync();
+    any_tile = true;
+  }
+
+  if (grad) {
+    // ---- per-CTA partial gradient straight out of TMEM (flat parameter layout of mlp.cuh)
+    float* out = p.partials + (size_t)blockIdx.x * kGradFloats;
+    if (!any_tile) {
+      for (int i = tid; i < kGradFloats; i += kTcThreads) out[i] = 0.f;
+    } else if (epi) {
+      // dW2 / db2: M = 64 accumulators, row o lives in the sample threads' lanes
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 16) {
+        float v[16];
+        tc::tmem_ld_x16(tmem_warp + kColDW2 + c, v);
+        tc::tmem_ld_wait();
+        if (is_sample)
+#pragma unroll
+          for (int j = 0; j < 16; j++) out[kOffW2 + s_loc * kHid + c + j] = v[j];
+      }
+      {
+        float v[16];
+        tc::tmem_ld_x16(tmem_warp + kColDB2, v);
+        tc::tmem_ld_wait();
+        if (is_sample) out[kOffB2 + s_loc] = v[12];
+      }
+      // dW1|db1 (rows 0..63) and dWc1|dbc1 (rows 64..127): M = 128, row = thread
+      {
+        float v[16];
+        tc::tmem_ld_x16(tmem_warp + kColDW1, v);
+        tc::tmem_ld_wait();
+        const int o = tid & 63;
+        const int offW = tid < 64 ? kOffW1 : kOffWc1, offB = tid < 64 ? kOffB1 : kOffBc1;
+#pragma unroll
+        for (int j = 0; j < kIn; j++) out[offW + o * kIn + j] = v[j];
+        out[offB + o] = v[12];
+      }
+      // rows 0..63 = C1 features -> dWc2 (column 4); rows 64..127 = A2 features -> dW3[k][feature] (columns 0..3)
+      {
+        float v[8];
+        tc::tmem_ld_x8(tmem_warp + kColDW3, v);
+        tc::tmem_ld_wait();
+        if (tid < 64) {
+          out[kOffWc2 + tid] = v[4];
+        } else {
+#pragma unroll
+          for (int k = 0; k < kAct; k++) out[kOffW3 + k * kHid + (tid - 64)] = v[k];
+        }
+      }
+    }
+    // db3, dbc2 and the loss sums: fixed-order block reduction of per-thread partials
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+      const float mine = pass < 4 ? db3_acc[pass] : pass == 4 ? dbc2_acc : pass == 5 ? lossV : pass == 6 ? lossA : skipped;
+      S.red[tid] = mine;
+      if (tid < 96) S.red[kTcThreads + tid] = 0.f;
+      __syncthreads();
+      for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) S.red[tid] += S.red[tid + w];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        const int dst = pass < 4 ? kOffB3 + pass : pass == 4 ? kOffBc2 : kTotalParams + (pass - 5);
+        out[dst] = S.red[0];
+      }
+      __syncthreads();
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+int tc_grid_for(int n, int sm_count) {
+  const int ntiles = (n + kS - 1) / kS;
+  return ntiles < sm_count ? (ntiles > 0 ? ntiles : 1) : sm_count;
+}
+
+cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ppo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  TcConsts gc;
+  gc.stdv = expf(p.log_std);
+  gc.neg_log_std = -logf(gc.stdv);
+  gc.log_sqrt_2pi = logf(sqrtf(2.0f * 3.14159274f));
+  gc.upper = 1.0f + p.epsilon;
+  gc.lower = 1.0f - p.epsilon;
+  gc.variance = gc.stdv * gc.stdv;
+  ppo_tc_kernel<<<grid, kTcThreads, sizeof(TcSmem), stream>>>(p, gc);
+  return cudaGetLastError();
+}
+
 }  // namespace wb

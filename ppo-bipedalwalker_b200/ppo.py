@@ -185,6 +185,10 @@ class PPOAgent:
     def sync(self):
         check(lib().wb_policy_sync(self._h))
 
+    def set_variant(self, variant: int):
+        """0: tcgen05 tensor-core kernel (default); 1: fp32 CUDA-core kernel."""
+        check(lib().wb_policy_set_variant(self._h, variant))
+
     def set_hyperparams(self, hp: Hyperparams):
         self.hp = hp
         check(lib().wb_policy_set_hyperparams(self._h, C.byref(hp)))

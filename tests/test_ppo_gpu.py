@@ -6,10 +6,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def make_pair(gpu, O, seed=0, batch_size=64):
+VARIANTS = [0, 1]  # 0: tcgen05 tensor-core kernel (3xTF32), 1: fp32 CUDA-core kernel
+
+
+def make_pair(gpu, O, seed=0, batch_size=64, variant=0):
     hp = gpu.default_hyperparams()
     hp.batch_size = batch_size
     agent = gpu.PPOAgent(hp=hp, seed=seed)
+    agent.set_variant(variant)
     actor = O.Net(12, O.ACTOR_LAYERS)
     critic = O.Net(12, O.CRITIC_LAYERS)
     actor.set_params(agent.actor.get_flat())
@@ -19,15 +23,38 @@ def make_pair(gpu, O, seed=0, batch_size=64):
     return agent, actor, critic, ohp
 
 
-def synth_batch(rng, actor, n, O=None, std=np.exp(np.float32(-1.0))):
+def keep_clear_of_leaky_kinks(states, actor_flat, critic_flat, margin=1e-5):
+    """LeakyReLU' jumps from 0.2 to 1 at a pre-activation of exactly 0: a sample with a hidden pre-activation within rounding
+    distance of 0 may legitimately take either slope depending on the summation order (with B = 65536 one such sample moves the
+    gradient by ~1e-3 relative).  Like the clip boundaries, such samples are replaced by a generic one (fp64 pre-activations)."""
+    s = states.astype(np.float64)
+    a = np.asarray(actor_flat, np.float64)
+    c = np.asarray(critic_flat, np.float64)
+    w1, b1 = a[:768].reshape(64, 12), a[768:832]
+    w2, b2 = a[832:832 + 4096].reshape(64, 64), a[832 + 4096:832 + 4160]
+    wc1, bc1 = c[:768].reshape(64, 12), c[768:832]
+    z1 = s @ w1.T + b1
+    z2 = np.maximum(0.2 * z1, z1) @ w2.T + b2
+    zc = s @ wc1.T + bc1
+    tight = np.minimum(np.minimum(np.abs(z1).min(1), np.abs(z2).min(1)), np.abs(zc).min(1)) < margin
+    if tight.any():
+        states[tight] = states[np.flatnonzero(~tight)[0]]
+    return states
+
+
+def synth_batch(rng, actor, n, O=None, std=np.exp(np.float32(-1.0)), critic_flat=None):
     """cfg3-style synthetic minibatch: scaled observations, actions near the mean, perturbed old log-probs."""
     scale = np.array([1, 1, 1, 1, 1, 1, 0.1, 0.1, 0.5, 0.5, 0.5, 0.5], np.float32)
     shift = np.array([0.14, 1.6, 0.13, 1.7, 0.13, 1.7, 0, 0, 0, 0, 0, 0], np.float32)
     states = (rng.normal(size=(n, 12)).astype(np.float32) * scale * 0.3 + shift).astype(np.float32)
+    if critic_flat is not None:
+        states = keep_clear_of_leaky_kinks(states, actor.get_params(), critic_flat)
     mean = actor.forward(states)
     actions = (mean + std * rng.normal(size=(n, 4))).astype(np.float32)
     logp = (-np.log(std) - np.log(np.sqrt(2 * np.pi)) - 0.5 * ((actions - mean) / std) ** 2).astype(np.float32)
     old_logp = (logp + 0.25 * rng.normal(size=(n, 4))).astype(np.float32)  # ratios straddle 1 +- 0.3
+    ratio = np.exp(logp.astype(np.float64) - old_logp)  # keep clear of the clip discontinuities (see the cross-kernel test)
+    old_logp[(np.abs(ratio - 1.3) < 1e-3) | (np.abs(ratio - 0.7) < 1e-3)] += np.float32(0.01)
     adv = rng.normal(size=n).astype(np.float32)
     ret = (5 * rng.normal(size=n)).astype(np.float32)
     return states, actions, old_logp, adv, ret
@@ -37,8 +64,9 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-def test_forward_matches_oracle(gpu, O):
-    agent, actor, critic, _ = make_pair(gpu, O, 1)
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_forward_matches_oracle(gpu, O, variant):
+    agent, actor, critic, _ = make_pair(gpu, O, 1, variant=variant)
     rng = np.random.default_rng(1)
     for n in (1, 63, 64, 65, 1000):
         s = rng.normal(size=(n, 12)).astype(np.float32)
@@ -47,8 +75,9 @@ def test_forward_matches_oracle(gpu, O):
         np.testing.assert_allclose(value, critic.forward(s)[:, 0], rtol=1e-5, atol=1e-6)
 
 
-def test_sample_actions_with_injected_uniforms(gpu, O):
-    agent, actor, critic, ohp = make_pair(gpu, O, 2)
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_sample_actions_with_injected_uniforms(gpu, O, variant):
+    agent, actor, critic, ohp = make_pair(gpu, O, 2, variant=variant)
     rng = np.random.default_rng(2)
     n = 300
     s = rng.normal(size=(n, 12)).astype(np.float32)
@@ -63,11 +92,12 @@ def test_sample_actions_with_injected_uniforms(gpu, O):
     assert np.allclose(std, np.exp(np.float32(-1)))
 
 
-@pytest.mark.parametrize("n,batch_size", [(64, 64), (100, 64), (4096, 4096)])
-def test_ppo_gradient_matches_oracle(gpu, O, n, batch_size):
-    agent, actor, critic, ohp = make_pair(gpu, O, 3, batch_size)
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n,batch_size", [(64, 64), (100, 64), (4096, 4096), (20000, 20000)])
+def test_ppo_gradient_matches_oracle(gpu, O, n, batch_size, variant):
+    agent, actor, critic, ohp = make_pair(gpu, O, 3, batch_size, variant=variant)
     rng = np.random.default_rng(n)
-    batch = synth_batch(rng, actor, n)
+    batch = synth_batch(rng, actor, n, critic_flat=critic.get_params())
     closs, aloss, skipped = agent.Gradients(*batch)
     rskip, rcl, ral = O.ppo_train_batch(actor, critic, ohp, *batch, optimise=False)
     assert skipped == rskip == 0
@@ -76,8 +106,9 @@ def test_ppo_gradient_matches_oracle(gpu, O, n, batch_size):
     assert abs(closs - rcl) <= 1e-4 * max(1.0, abs(rcl)) and abs(aloss - ral) <= 1e-4 * max(1.0, abs(ral))
 
 
-def test_skipped_sample_when_old_probability_underflows(gpu, O):
-    agent, actor, critic, ohp = make_pair(gpu, O, 4)
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_skipped_sample_when_old_probability_underflows(gpu, O, variant):
+    agent, actor, critic, ohp = make_pair(gpu, O, 4, variant=variant)
     rng = np.random.default_rng(4)
     states, actions, old_logp, adv, ret = synth_batch(rng, actor, 64)
     old_logp[5, 2] = -200.0  # exp underflows to 0 -> HadamardDivision throws -> sample skipped (PPOAgent.cs:286-290)
@@ -88,8 +119,9 @@ def test_skipped_sample_when_old_probability_underflows(gpu, O):
     assert rel_err(agent.critic.get_grads(), critic.get_grads()) < 1e-4
 
 
-def test_adam_steps_track_oracle(gpu, O):
-    agent, actor, critic, ohp = make_pair(gpu, O, 5)
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_adam_steps_track_oracle(gpu, O, variant):
+    agent, actor, critic, ohp = make_pair(gpu, O, 5, variant=variant)
     rng = np.random.default_rng(5)
     for it in range(5):
         batch = synth_batch(rng, actor, 64)
@@ -185,3 +217,38 @@ def test_train_one_episode_end_to_end(gpu, O):
     if len(traj.States) >= 64:
         assert not np.array_equal(before, agent.actor.get_flat())
     assert np.isfinite(agent.actor.get_flat()).all()
+
+
+def test_tensor_core_and_cuda_core_kernels_agree(gpu, O):
+    """Two independent kernels for the same path (tcgen05 3xTF32 vs fp32 FMA) on a 65536-sample minibatch."""
+    rng = np.random.default_rng(11)
+    hp = gpu.default_hyperparams()
+    hp.batch_size = 65536
+    a0 = gpu.PPOAgent(hp=hp, seed=12)
+    a1 = gpu.PPOAgent(hp=hp, seed=12)
+    a1.set_variant(1)
+    actor = O.Net(12, O.ACTOR_LAYERS)
+    actor.set_params(a0.actor.get_flat())
+    n = 65536
+    states = keep_clear_of_leaky_kinks(rng.normal(size=(n, 12)).astype(np.float32), a0.actor.get_flat(), a0.critic.get_flat())
+    mean, _ = a1.FeedForward(states)
+    std = np.exp(np.float32(-1.0))
+    actions = (mean + std * rng.normal(size=(n, 4))).astype(np.float32)
+    logp = (-np.log(std) - np.log(np.sqrt(2 * np.pi)) - 0.5 * ((actions - mean) / std) ** 2).astype(np.float32)
+    old = (logp + 0.2 * rng.normal(size=(n, 4))).astype(np.float32)
+    # the clipped surrogate is discontinuous at ratio = 1 +- epsilon: a sample within rounding distance of a boundary may
+    # legitimately take either branch, so keep every ratio at least 1e-3 away from both boundaries
+    ratio = np.exp(logp.astype(np.float64) - old)
+    near = (np.abs(ratio - 1.3) < 1e-3) | (np.abs(ratio - 0.7) < 1e-3)
+    old[near] += np.float32(0.01)
+    adv = rng.normal(size=n).astype(np.float32)
+    ret = (5 * rng.normal(size=n)).astype(np.float32)
+    l0 = a0.Gradients(states, actions, old, adv, ret)
+    l1 = a1.Gradients(states, actions, old, adv, ret)
+    assert rel_err(a0.actor.get_grads(), a1.actor.get_grads()) < 1e-4
+    assert rel_err(a0.critic.get_grads(), a1.critic.get_grads()) < 1e-4
+    assert abs(l0[0] - l1[0]) <= 1e-4 * max(1, abs(l1[0])) and abs(l0[1] - l1[1]) <= 1e-4 * max(1, abs(l1[1]))
+    m0, v0 = a0.FeedForward(states[:5000])
+    m1, v1 = a1.FeedForward(states[:5000])
+    np.testing.assert_allclose(m0, m1, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(v0, v1, rtol=1e-5, atol=2e-6)
