@@ -110,6 +110,41 @@ static void build_scene_constants(float* init92, float* floor10) {
   centroid_of(fl, 4, floor10 + 8);
 }
 
+// the floor's derived constants (see FloorConst): bounding box, edge normals, own projections -- same operation order as
+// BoundingBox.FindSignificantCorners (Skeleton.cs:144-176), SATCollision.AxisChecks/ProjectPoints (SATCollision.cs:39-76)
+static void build_floor_constants(const float* floor10, FloorConst* fc) {
+  memset(fc, 0, sizeof(*fc));
+  float minx = 3.402823466e+38f, miny = 3.402823466e+38f, maxx = -3.402823466e+38f, maxy = -3.402823466e+38f;
+  for (int i = 0; i < 4; i++) {
+    fc->v[i] = make_float2(floor10[2 * i], floor10[2 * i + 1]);
+    if (fc->v[i].x > maxx) maxx = fc->v[i].x;
+    if (fc->v[i].y > maxy) maxy = fc->v[i].y;
+    if (fc->v[i].x < minx) minx = fc->v[i].x;
+    if (fc->v[i].y < miny) miny = fc->v[i].y;
+  }
+  fc->cen = make_float2(floor10[8], floor10[9]);
+  fc->bb_min = make_float2(minx, miny);
+  fc->bb_max = make_float2(maxx, maxy);
+  for (int i = 0; i < 4; i++) {
+    const float2 p0 = fc->v[i], p1 = fc->v[(i + 1) % 4];
+    const float ex = f_sub(p1.x, p0.x), ey = f_sub(p1.y, p0.y);
+    float ax = -ey, ay = ex;
+    fc->skip[i] = (ax == 0.0f && ay == 0.0f) ? 1 : 0;
+    const float val = f_div(1.0f, sqrtf(f_add(f_mul(ax, ax), f_mul(ay, ay))));  // Vector2.Normalize
+    ax = f_mul(ax, val);
+    ay = f_mul(ay, val);
+    fc->axis[i] = make_float2(ax, ay);
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+    for (int j = 0; j < 4; j++) {
+      const float t = f_add(f_mul(ax, fc->v[j].x), f_mul(ay, fc->v[j].y));
+      if (t < mn) mn = t;
+      if (t > mx) mx = t;
+    }
+    fc->pmin[i] = mn;
+    fc->pmax[i] = mx;
+  }
+}
+
 }  // namespace wb
 
 using namespace wb;
@@ -119,7 +154,7 @@ struct wb_env_batch {
   int device = 0;
   cudaStream_t stream = nullptr;
   wb_hyperparams hp{};
-  int lanes = 16;
+  int lanes = 1;  // kernel variant: 1 = one thread per environment (default), 16 / 32 = cooperative lanes per environment
   int64_t launches = 0;
   // device state (structure of arrays)
   float* d_state = nullptr;    // [92][n_pad]
@@ -215,7 +250,10 @@ static int32_t launch(wb_env_batch* env, int phases, float dt, const float* d_ac
   p.iterations = env->hp.iterations;
   p.max_timesteps = env->hp.max_timesteps;
   p.phases = phases;
-  WB_CUDA(launch_physics(p, env->lanes, d_pt != nullptr || d_jt != nullptr, env->stream));
+  if (env->lanes == 1)
+    WB_CUDA(launch_physics_scalar(p, d_pt != nullptr || d_jt != nullptr, env->stream));
+  else
+    WB_CUDA(launch_physics(p, env->lanes, d_pt != nullptr || d_jt != nullptr, env->stream));
   env->launches++;
   return WB_OK;
 }
@@ -249,10 +287,14 @@ int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const u
       }
     }
     WB_CUDA(upload_materials(g_materials, WB_MAX_MATERIALS));
+    WB_CUDA(upload_materials_scalar(g_materials, WB_MAX_MATERIALS));
   }
   float floor10[10];
+  FloorConst floor_const;
   build_scene_constants(env->init92, floor10);
+  build_floor_constants(floor10, &floor_const);
   WB_CUDA(upload_scene_constants(env->init92, floor10));
+  WB_CUDA(upload_scene_constants_scalar(env->init92, &floor_const));
   WB_CUDA(cudaMalloc(&env->d_state, sizeof(float) * kStateFloats * np));
   WB_CUDA(cudaMalloc(&env->d_flags, sizeof(int32_t) * np));
   WB_CUDA(cudaMalloc(&env->d_steps, sizeof(int32_t) * np));
@@ -323,8 +365,9 @@ int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out) {
 
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env) {
   WB_REQUIRE(env, "env is null");
-  if (lanes_per_env == 0) lanes_per_env = 16;
-  if (lanes_per_env != 16 && lanes_per_env != 32) return fail(WB_ERR_INVALID, "lanes_per_env must be 16 or 32");
+  if (lanes_per_env == 0) lanes_per_env = 1;
+  if (lanes_per_env != 1 && lanes_per_env != 16 && lanes_per_env != 32)
+    return fail(WB_ERR_INVALID, "lanes_per_env must be 1, 16 or 32");
   env->lanes = lanes_per_env;
   return WB_OK;
 }

@@ -17,6 +17,7 @@
 // division, and double-precision sin/cos rounded to float for Skeleton.Rotate -- the same operation order
 // as the reference's C# (SURVEY.md Appendix A/C).  There is no CPU path.
 #include "physics.cuh"
+#include "physics_math.cuh"
 
 #include <cfloat>
 
@@ -46,111 +47,6 @@ __device__ __forceinline__ int record_to_smem(int f) {
   return f + (f >= 34 ? 2 : 0) + (f >= 58 ? 12 : 0) + (f >= 68 ? 2 : 0);
 }
 
-// ---------------------------------------------------------------- exact fp32 helpers (never fused)
-__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }          // 1f / a, correctly rounded
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
-
-__device__ __forceinline__ float2 mk2(float x, float y) { return make_float2(x, y); }
-__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return mk2(fadd(a.x, b.x), fadd(a.y, b.y)); }
-__device__ __forceinline__ float2 vsub(float2 a, float2 b) { return mk2(fsub(a.x, b.x), fsub(a.y, b.y)); }
-__device__ __forceinline__ float2 vneg(float2 a) { return mk2(-a.x, -a.y); }
-__device__ __forceinline__ float2 vmul(float2 a, float s) { return mk2(fmul(a.x, s), fmul(a.y, s)); }
-__device__ __forceinline__ float2 vhalf(float2 a) { return mk2(fmul(a.x, 0.5f), fmul(a.y, 0.5f)); }  // Vector2 / 2: factor = 1f/2f
-__device__ __forceinline__ float vdot(float2 a, float2 b) { return fadd(fmul(a.x, b.x), fmul(a.y, b.y)); }
-__device__ __forceinline__ float2 vnormalize(float2 a) {  // Vector2.Normalize: val = 1f / sqrt(x*x + y*y)
-  float val = frcp(fsqrt(fadd(fmul(a.x, a.x), fmul(a.y, a.y))));
-  return mk2(fmul(a.x, val), fmul(a.y, val));
-}
-__device__ __forceinline__ float2 lds2(const float* s, int off) { return *reinterpret_cast<const float2*>(s + off); }
-__device__ __forceinline__ void sts2(float* s, int off, float2 v) { *reinterpret_cast<float2*>(s + off) = v; }
-
-// .NET Math.Max / Math.Min (float): IEEE-754-2019 maximum/minimum, NaN-propagating
-__device__ __forceinline__ float net_max(float a, float b) {
-  if (a != b) return (a != a) ? a : (b < a ? a : b);
-  return signbit(b) ? a : b;
-}
-__device__ __forceinline__ float net_min(float a, float b) {
-  if (a != b) return (a != a) ? a : (a < b ? a : b);
-  return signbit(a) ? a : b;
-}
-
-// ---- (float)Math.Cos((double)r), (float)Math.Sin((double)r) for Matrix.CreateRotationZ (MonoGame)
-// double-double helpers for the (rare) slow path
-struct dd { double hi, lo; };
-__device__ __forceinline__ dd dd_two_sum(double a, double b) { double s = a + b, bb = s - a; return {s, (a - (s - bb)) + (b - bb)}; }
-__device__ __forceinline__ dd dd_mul(dd a, dd b) {
-  double p = a.hi * b.hi, e = fma(a.hi, b.hi, -p) + (a.hi * b.lo + a.lo * b.hi);
-  double s = p + e; return {s, e - (s - p)};
-}
-__device__ __forceinline__ dd dd_add(dd a, dd b) {
-  dd s = dd_two_sum(a.hi, b.hi); double e = s.lo + (a.lo + b.lo); double h = s.hi + e; return {h, e - (h - s.hi)};
-}
-__device__ __forceinline__ dd dd_div_int(dd a, double n) {  // a / n for a small integer n
-  double q = a.hi / n; double r = fma(-q, n, a.hi) + a.lo; double q2 = r / n; double h = q + q2; return {h, q2 - (h - q)};
-}
-// correctly rounded float of a double-double: only an exact float-midpoint in hi needs lo to break the tie
-__device__ __forceinline__ float dd_to_float(dd v) {
-  long long b = __double_as_longlong(v.hi);
-  if (((unsigned)b & 0x1FFFFFFFu) == 0x10000000u && v.lo != 0.0) b += ((v.lo > 0.0) == (v.hi > 0.0)) ? 1 : -1;
-  return (float)__longlong_as_double(b);
-}
-// sin/cos of |x| < 2^-5 in double-double (Taylor series, ~100 bits): only used when the fast result is within one double
-// ulp of a float rounding boundary, so that the float we return is the correctly rounded one.
-__device__ __noinline__ void sincos_dd_small(double x, float& c, float& s) {
-  const dd X = {x, 0.0};
-  const dd X2 = dd_mul(X, X);
-  dd term = X, sum = X;  // sin: x - x^3/3! + x^5/5! - ...
-#pragma unroll 1
-  for (int k = 1; k <= 9; k++) {
-    term = dd_div_int(dd_mul(term, X2), -(double)((2 * k) * (2 * k + 1)));
-    sum = dd_add(sum, term);
-  }
-  s = dd_to_float(sum);
-  term = {1.0, 0.0};
-  sum = {1.0, 0.0};      // cos: 1 - x^2/2! + x^4/4! - ...
-#pragma unroll 1
-  for (int k = 1; k <= 9; k++) {
-    term = dd_div_int(dd_mul(term, X2), -(double)((2 * k - 1) * (2 * k)));
-    sum = dd_add(sum, term);
-  }
-  c = dd_to_float(sum);
-}
-
-// true when the double r is within one ulp of the midpoint between two adjacent floats (its rounding to float is then
-// not decided by a <=0.5-ulp-accurate double)
-__device__ __forceinline__ bool float_rounding_ambiguous(double r) {
-  const unsigned lo = (unsigned)__double2loint(r) & 0x1FFFFFFFu;  // the 29 mantissa bits a float drops
-  return (lo - 0x0FFFFFFFu) <= 2u;
-}
-
-__device__ __forceinline__ void rotz(float radians, float& c, float& s) {
-  const double x = (double)radians;
-  if (fabsf(radians) < 0.03125f) {
-    // per-substep angles are tiny (omega * 3.3e-4): Taylor polynomials in double, truncation error < 2^-70 relative,
-    // total error ~0.5 ulp -- at least as accurate as a libm call, so the float rounding matches a correctly rounded libm
-    const double x2 = x * x;
-    double ps = fma(x2, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
-    ps = fma(x2, ps, 8.3333333333333332e-03);                               // 1/5!
-    ps = fma(x2, ps, -1.6666666666666666e-01);                              // -1/3!
-    const double sd = fma(x * x2, ps, x);
-    double pc = fma(x2, 2.4801587301587302e-05, -1.3888888888888889e-03);   // 1/8!, -1/6!
-    pc = fma(x2, pc, 4.1666666666666664e-02);                               // 1/4!
-    pc = fma(x2, pc, -0.5);
-    const double cd = fma(x2, pc, 1.0);
-    c = (float)cd;
-    s = (float)sd;
-    if (float_rounding_ambiguous(cd) || (float_rounding_ambiguous(sd) && fabsf(radians) > 1e-30f)) sincos_dd_small(x, c, s);
-    return;
-  }
-  double sd, cd;
-  sincos(x, &sd, &cd);
-  c = (float)cd;
-  s = (float)sd;
-}
 
 // ---------------------------------------------------------------- per-group context
 struct Ctx {

@@ -8,6 +8,7 @@
 namespace wb {
 
 constexpr int kEnvsPerCta = 8;    // environments staged per CTA (one 32-byte sector per SoA row)
+constexpr int kScalarEnvsPerCta = 128;  // thread-per-environment kernel (physics_scalar.cu): environments per CTA
 constexpr int kStateFloats = WB_STATE_FLOATS;
 
 struct Material {
@@ -46,6 +47,23 @@ struct PhysicsParams {
   int32_t max_timesteps;
   int32_t phases;
 };
+
+// Environment.CreateFloor (Environment.cs:211-226) and everything about the static floor that never changes, computed once
+// on the host with the reference's formulas (strict fp32): vertices, cached centroid, bounding box, the normalised left
+// normals of its edges (SATCollision.cs:43-46) and its own projection onto each of them (SATCollision.cs:63-76)
+struct FloorConst {
+  float2 v[4];
+  float2 cen;
+  float2 bb_min, bb_max;
+  float2 axis[4];
+  float pmin[4], pmax[4];
+  int32_t skip[4];  // axis == Vector2.Zero: skipped by AxisChecks
+};
+
+// thread-per-environment kernel (physics_scalar.cu)
+cudaError_t upload_materials_scalar(const Material* table, int count);
+cudaError_t upload_scene_constants_scalar(const float* init_state92, const FloorConst* floor);
+cudaError_t launch_physics_scalar(const PhysicsParams& p, bool trace, cudaStream_t stream);
 
 // host-side helpers implemented in physics.cu
 cudaError_t upload_materials(const Material* table, int count);

@@ -22,4 +22,4 @@ e0.record()
 for _ in range(K): env.step_dev(a, obs, rew, done)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print(f"n={n} lanes={lanes or 16} {ms:.3f} ms/step  {n/ms*1e3:.3e} env-steps/s  done_frac={done.float().mean().item():.3f}")
+print(f"n={n} lanes={lanes or 1} {ms:.3f} ms/step  {n/ms*1e3:.3e} env-steps/s  done_frac={done.float().mean().item():.3f}")
