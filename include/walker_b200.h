@@ -148,6 +148,11 @@ int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env);
  * Skeleton.Rotate (Skeleton.cs:93). mode 0: production path, 1: forced double-double path, 2: forced device sincos path */
 int32_t wb_debug_rotz(int32_t n, const float* radians_host, int32_t mode, float* cos_host, float* sin_host);
 
+/* test hook: the kernels evaluate Vector2.Normalize's factor 1f / sqrt(s) (two correctly rounded steps, MonoGame Vector2.Normalize as
+ * used by SATCollision.cs:46, ContactPoints.cs:27,84,86, Joint.cs:36) with a branch-free sequence; this compares it with the
+ * two-intrinsic form for every float bit pattern in [first_bits, first_bits + count) and returns the number of mismatches */
+int32_t wb_debug_rcp_sqrt_check(uint32_t first_bits, uint64_t count, uint64_t* mismatches_out, uint32_t* first_bad_bits_out);
+
 /* ---- policy: Walker/PPO/PPOAgent.cs, Network/, Matrix.cs ---- */
 /* layer kinds of the network DSL (PPOAgent.ParseLayers, PPOAgent.cs:96-143) */
 enum { WB_DENSE = 0, WB_RELU = 1, WB_LEAKYRELU = 2, WB_TANH = 3 };

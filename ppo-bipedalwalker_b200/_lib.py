@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         "wb_env_launch_count": (C.c_int32, [vp, i64p]),
         "wb_env_set_variant": (C.c_int32, [vp, C.c_int32]),
         "wb_debug_rotz": (C.c_int32, [C.c_int32, vp, C.c_int32, vp, vp]),
+        "wb_debug_rcp_sqrt_check": (C.c_int32, [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
         "wb_policy_create": (C.c_int32, [C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, hpp, C.POINTER(vp)]),
         "wb_policy_destroy": (C.c_int32, [vp]),
         "wb_policy_set_stream": (C.c_int32, [vp, vp]),

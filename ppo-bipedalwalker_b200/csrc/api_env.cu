@@ -507,4 +507,24 @@ int32_t wb_debug_rotz(int32_t n, const float* radians_host, int32_t mode, float*
   return WB_OK;
 }
 
+int32_t wb_debug_rcp_sqrt_check(uint32_t first_bits, uint64_t count, uint64_t* mismatches_out, uint32_t* first_bad_bits_out) {
+  WB_REQUIRE(mismatches_out && first_bad_bits_out, "null argument");
+  if (int32_t rc = require_device()) return rc;
+  unsigned long long* d_cnt = nullptr;
+  uint32_t* d_bad = nullptr;
+  WB_CUDA(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+  WB_CUDA(cudaMalloc(&d_bad, sizeof(uint32_t)));
+  cudaError_t e = cudaMemset(d_cnt, 0, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(d_bad, 0xFF, sizeof(uint32_t));
+  if (e == cudaSuccess) e = launch_rcp_sqrt_check(first_bits, count, d_cnt, d_bad, nullptr);
+  unsigned long long cnt = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(first_bad_bits_out, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_cnt);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return fail(WB_ERR_CUDA, "wb_debug_rcp_sqrt_check: %s", cudaGetErrorString(e));
+  *mismatches_out = cnt;
+  return WB_OK;
+}
+
 }  // extern "C"

@@ -64,6 +64,8 @@ struct FloorConst {
 cudaError_t upload_materials_scalar(const Material* table, int count);
 cudaError_t upload_scene_constants_scalar(const float* init_state92, const FloorConst* floor);
 cudaError_t launch_physics_scalar(const PhysicsParams& p, bool trace, cudaStream_t stream);
+cudaError_t launch_rcp_sqrt_check(uint32_t first, uint64_t count, unsigned long long* mismatches_dev, uint32_t* first_bad_dev,
+                                  cudaStream_t stream);
 
 // host-side helpers implemented in physics.cu
 cudaError_t upload_materials(const Material* table, int count);

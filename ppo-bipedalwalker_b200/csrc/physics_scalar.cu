@@ -145,7 +145,7 @@ __device__ __forceinline__ void joint_step(const Env& e, int A, int ia, int B, i
     }
   }
   if (depth < 0.1f) return;
-  ab = vnormalize(ab);
+  ab = vnormalize_fast(ab);
   const float2 dA = vhalf(vmul(ab, depth));
   const float2 dB = vhalf(vmul(vneg(ab), depth));
   move_body(e, A, dA);
@@ -183,13 +183,15 @@ struct Sat {
   bool sep;  // an axis separated the polygons: AxisChecks returned false (every later axis is ignored)
 };
 
-// one iteration of the AxisChecks loop body after the projections (SATCollision.cs:47-56); symmetric in the two projections
+// one iteration of the AxisChecks loop body after the projections (SATCollision.cs:47-56); symmetric in the two projections.
+// Once an axis separates, the reference returns false and nothing computed afterwards is used, so only `sep` needs guarding;
+// a skipped (zero) axis has NaN projections and must not touch anything.  "tempDepth >= depth -> continue" keeps the FIRST
+// minimal axis: update only on a strictly smaller depth (temp is never NaN on a live, overlapping axis).
 __device__ __forceinline__ void sat_accumulate(Sat& s, bool skip, float2 axis, int idx, float omin, float omax, float tmin, float tmax) {
   const float temp = fminf(fsub(tmax, omin), fsub(omax, tmin));
   const bool overlapping = (omin < tmax) && (tmin < omax);
-  const bool live = !skip && !s.sep;
-  if (live && !overlapping) s.sep = true;
-  if (live && overlapping && !(temp >= s.depth)) {  // "tempDepth >= depth -> continue": the first minimal axis wins
+  s.sep = s.sep || (!skip && !overlapping);
+  if (!skip && temp < s.depth) {
     s.depth = temp;
     s.normal = axis;
     s.idx = idx;
@@ -201,7 +203,7 @@ __device__ __forceinline__ float2 edge_axis(float2 p0, float2 p1, bool& skip) {
   const float2 edge = vsub(p1, p0);
   const float2 axis = mk2(-edge.y, edge.x);
   skip = (axis.x == 0.0f) && (axis.y == 0.0f);
-  return vnormalize(axis);
+  return vnormalize_fast(axis);
 }
 
 // ---------------------------------------------------------------- contact points, ContactPoints.cs:13-134
@@ -211,8 +213,8 @@ struct Face {
 
 // GetSignificantFace given the support vertex sv = P[k] and its neighbours (ContactPoints.cs:79-94)
 __device__ __forceinline__ Face face_from(float2 sv, float2 next, float2 prev, float2 nrm) {
-  const float2 after = vnormalize(vsub(sv, next));
-  const float2 before = vnormalize(vsub(sv, prev));
+  const float2 after = vnormalize_fast(vsub(sv, next));
+  const float2 before = vnormalize_fast(vsub(sv, prev));
   const bool use_before = vdot(nrm, before) >= vdot(nrm, after);
   Face f;
   f.a = use_before ? sv : next;
@@ -292,7 +294,7 @@ __device__ __forceinline__ int contact_points(Face ref, Face inc, float2 normal,
     inc = t;
     rf = vsub(ref.b, ref.a);
   }
-  rf = vnormalize(rf);
+  rf = vnormalize_fast(rf);
   float offset = vdot(rf, ref.a);
   float2 p0 = mk2(0.f, 0.f), p1 = mk2(0.f, 0.f);
   int cnt = clip_vectors(inc.a, inc.b, rf, offset, p0, p1);
@@ -395,25 +397,20 @@ __device__ __forceinline__ void pole_pair(Env& e, int A, int B, wb_pair_trace* t
     s.normal = mk2(0.0f, 0.0f);
     s.idx = -1;
     s.sep = false;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {  // AxisChecks(A, B): axes from A's edges
+    // AxisChecks(A, B) then, only while nothing separated, AxisChecks(B, A): one loop over the 12 edges.  The polygons stay in
+    // registers for the projections; only the two edge endpoints are fetched by (runtime) index.  A lane leaves the loop at its
+    // first separating axis, exactly like the reference's early "return false".
+    const int nA = nverts(A);
+#pragma unroll 1
+    for (int i = 0; i < 12 && !s.sep; i++) {
+      const int own = i < 6 ? A : B;
+      const int k = i < 6 ? i : i - 6;
       bool skip;
-      const float2 axis = edge_axis(PA[i], PA[(i + 1) % 6], skip);
-      float omin, omax, tmin, tmax;
-      project6(PA, axis, omin, omax);
-      project6(PB, axis, tmin, tmax);
-      sat_accumulate(s, skip, axis, i, omin, omax, tmin, tmax);
-    }
-    if (!s.sep) {
-#pragma unroll
-      for (int i = 0; i < 6; i++) {  // AxisChecks(B, A): only when the first call returned true
-        bool skip;
-        const float2 axis = edge_axis(PB[i], PB[(i + 1) % 6], skip);
-        float omin, omax, tmin, tmax;
-        project6(PB, axis, omin, omax);
-        project6(PA, axis, tmin, tmax);
-        sat_accumulate(s, skip, axis, 6 + i, omin, omax, tmin, tmax);
-      }
+      const float2 axis = edge_axis(V2(e, own * 6 + k), V2(e, own * 6 + (k == 5 ? 0 : k + 1)), skip);
+      float amn, amx, bmn, bmx;
+      project6(PA, axis, amn, amx);
+      project6(PB, axis, bmn, bmx);
+      sat_accumulate(s, skip, axis, i < 6 ? i : nA + k, amn, amx, bmn, bmx);
     }
     if (!s.sep) {
       // orient: normal points from B towards A (SATCollision.cs:31-32, cached centroids)
@@ -462,23 +459,21 @@ __device__ __forceinline__ void floor_pair(Env& e, int A, wb_pair_trace* tr) {
     s.normal = mk2(0.0f, 0.0f);
     s.idx = -1;
     s.sep = false;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {  // AxisChecks(A, floor)
+#pragma unroll 1
+    for (int i = 0; i < 6 && !s.sep; i++) {  // AxisChecks(A, floor)
       bool skip;
-      const float2 axis = edge_axis(PA[i], PA[(i + 1) % 6], skip);
+      const float2 axis = edge_axis(V2(e, A * 6 + i), V2(e, A * 6 + (i == 5 ? 0 : i + 1)), skip);
       float omin, omax, tmin, tmax;
       project6(PA, axis, omin, omax);
       project_floor(axis, tmin, tmax);
       sat_accumulate(s, skip, axis, i, omin, omax, tmin, tmax);
     }
-    if (!s.sep) {
-      const int nA = nverts(A);
-#pragma unroll
-      for (int i = 0; i < 4; i++) {  // AxisChecks(floor, A): constant axes and constant own projection
-        float tmin, tmax;
-        project6(PA, c_floor.axis[i], tmin, tmax);
-        sat_accumulate(s, c_floor.skip[i] != 0, c_floor.axis[i], nA + i, c_floor.pmin[i], c_floor.pmax[i], tmin, tmax);
-      }
+    const int nA = nverts(A);
+#pragma unroll 1
+    for (int i = 0; i < 4 && !s.sep; i++) {  // AxisChecks(floor, A): constant axes and constant own projection
+      float tmin, tmax;
+      project6(PA, c_floor.axis[i], tmin, tmax);
+      sat_accumulate(s, c_floor.skip[i] != 0, c_floor.axis[i], nA + i, c_floor.pmin[i], c_floor.pmax[i], tmin, tmax);
     }
     if (!s.sep) {
       BodyDyn X = load_dyn(e, A);
@@ -722,9 +717,33 @@ __global__ void __launch_bounds__(kT, 4) physics_scalar_kernel(const PhysicsPara
   for (int f = 0; f < 88; f++) p.state[(size_t)f * p.n_pad + env] = record_ref(e, f);
 }
 
+// test hook: compares rcp_sqrt_rn(s) with __frcp_rn(__fsqrt_rn(s)) for every bit pattern in [first, first + count)
+__global__ void rcp_sqrt_check_kernel(uint32_t first, uint64_t count, unsigned long long* mismatches, uint32_t* first_bad) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint32_t bits = first + (uint32_t)i;
+    const float s = __uint_as_float(bits);
+    const uint32_t a = __float_as_uint(rcp_sqrt_rn(s));
+    const uint32_t b = __float_as_uint(__frcp_rn(__fsqrt_rn(s)));
+    const bool both_nan = ((a & 0x7FFFFFFFu) > 0x7F800000u) && ((b & 0x7FFFFFFFu) > 0x7F800000u);
+    if (a != b && !both_nan) {
+      bad++;
+      atomicMin(first_bad, bits);
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace t1
 
 // ---------------------------------------------------------------- host side
+cudaError_t launch_rcp_sqrt_check(uint32_t first, uint64_t count, unsigned long long* mismatches_dev, uint32_t* first_bad_dev,
+                                  cudaStream_t stream) {
+  t1::rcp_sqrt_check_kernel<<<148 * 8, 256, 0, stream>>>(first, count, mismatches_dev, first_bad_dev);
+  return cudaGetLastError();
+}
+
 cudaError_t upload_materials_scalar(const Material* table, int count) {
   return cudaMemcpyToSymbol(t1::c_materials, table, sizeof(Material) * count);
 }

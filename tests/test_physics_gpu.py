@@ -231,3 +231,14 @@ def test_kernel_variants_bit_exact(gpu, O, lanes):
             robs, rrew, rdone = ref.step(a)
             assert np.array_equal(bits(obs), bits(robs)) and np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone)
     assert_state_equal(env, ref, f"lanes={lanes}")
+
+
+def test_branch_free_normalize_factor_is_exhaustively_exact(gpu):
+    """rcp_sqrt_rn(s) (one MUFU.RSQ + 4 FMAs, what the thread-per-env kernel uses for Vector2.Normalize's 1f / sqrt(s)) equals
+    __frcp_rn(__fsqrt_rn(s)) for EVERY one of the 2^32 float bit patterns."""
+    import ctypes as C
+    from ppo_bipedalwalker_b200._lib import check, lib
+    bad = C.c_uint64(0)
+    first = C.c_uint32(0)
+    check(lib().wb_debug_rcp_sqrt_check(0, 1 << 32, C.byref(bad), C.byref(first)))
+    assert bad.value == 0, f"{bad.value} mismatches, first at bits 0x{first.value:08x}"
