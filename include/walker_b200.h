@@ -140,8 +140,8 @@ int32_t wb_env_step_dev(wb_env_batch* env, const float* actions_dev, float delta
                         float* reward_dev, uint8_t* done_dev);
 /* number of kernel launches this handle has issued (bench.py "gpu_launches") */
 int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out);
-/* which kernel variant this handle uses: lanes per environment -- 1 = one thread per environment (library default),
- * 16 / 32 = cooperative lanes per environment; 0 = library default */
+/* lanes per environment of the physics kernel: 1 (one thread per walker: throughput, large batches), 2, 4, 8 or 16 (the lanes of
+ * a walker split its SAT axes and vertices: latency, small batches); 0 = chosen from the batch size (the default) */
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env);
 
 /* test hook: the rotation coefficients (float)Math.Cos((double)r), (float)Math.Sin((double)r) of Matrix.CreateRotationZ as used by

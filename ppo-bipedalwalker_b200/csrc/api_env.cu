@@ -149,12 +149,23 @@ static void build_floor_constants(const float* floor10, FloorConst* fc) {
 
 using namespace wb;
 
+// Lanes per environment when the caller does not choose: with few walkers per SM the step is latency bound and the lanes of
+// a walker split its SAT axes and vertices; with many, one lane per walker does no redundant work (see physics_lanes.cu).
+static int default_lanes(int n_envs, int sm_count) {
+  const long per_sm = ((long)n_envs + sm_count - 1) / sm_count;
+  if (per_sm <= 64) return 8;
+  if (per_sm <= 160) return 4;
+  if (per_sm <= 320) return 2;
+  return 1;
+}
+
 struct wb_env_batch {
   int32_t n = 0, n_pad = 0;
   int device = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   wb_hyperparams hp{};
-  int lanes = 1;  // kernel variant: 1 = one thread per environment (default), 16 / 32 = cooperative lanes per environment
+  int lanes = 0;  // lanes per environment (1, 2, 4, 8, 16); 0 = chosen from the batch size at creation
   int64_t launches = 0;
   // device state (structure of arrays)
   float* d_state = nullptr;    // [92][n_pad]
@@ -250,10 +261,7 @@ static int32_t launch(wb_env_batch* env, int phases, float dt, const float* d_ac
   p.iterations = env->hp.iterations;
   p.max_timesteps = env->hp.max_timesteps;
   p.phases = phases;
-  if (env->lanes == 1)
-    WB_CUDA(launch_physics_scalar(p, d_pt != nullptr || d_jt != nullptr, env->stream));
-  else
-    WB_CUDA(launch_physics(p, env->lanes, d_pt != nullptr || d_jt != nullptr, env->stream));
+  WB_CUDA(launch_physics(p, env->lanes, d_pt != nullptr || d_jt != nullptr, env->stream));
   env->launches++;
   return WB_OK;
 }
@@ -267,8 +275,10 @@ int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const u
   wb_env_batch* env = new (std::nothrow) wb_env_batch();
   WB_REQUIRE(env, "out of host memory");
   cudaGetDevice(&env->device);
+  cudaDeviceGetAttribute(&env->sm_count, cudaDevAttrMultiProcessorCount, env->device);
   env->n = n_envs;
-  env->n_pad = (n_envs + kEnvsPerCta - 1) / kEnvsPerCta * kEnvsPerCta;
+  env->lanes = default_lanes(n_envs, env->sm_count);
+  env->n_pad = (n_envs + kEnvPad - 1) / kEnvPad * kEnvPad;
   if (hp) env->hp = *hp; else wb_hyperparams_default(&env->hp);
   if (env->hp.iterations <= 0 || env->hp.iterations >= 200) {  // Hyperparameters.cs:189-217 range check
     delete env;
@@ -287,14 +297,12 @@ int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const u
       }
     }
     WB_CUDA(upload_materials(g_materials, WB_MAX_MATERIALS));
-    WB_CUDA(upload_materials_scalar(g_materials, WB_MAX_MATERIALS));
   }
   float floor10[10];
   FloorConst floor_const;
   build_scene_constants(env->init92, floor10);
   build_floor_constants(floor10, &floor_const);
-  WB_CUDA(upload_scene_constants(env->init92, floor10));
-  WB_CUDA(upload_scene_constants_scalar(env->init92, &floor_const));
+  WB_CUDA(upload_scene_constants(env->init92, &floor_const));
   WB_CUDA(cudaMalloc(&env->d_state, sizeof(float) * kStateFloats * np));
   WB_CUDA(cudaMalloc(&env->d_flags, sizeof(int32_t) * np));
   WB_CUDA(cudaMalloc(&env->d_steps, sizeof(int32_t) * np));
@@ -365,9 +373,8 @@ int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out) {
 
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env) {
   WB_REQUIRE(env, "env is null");
-  if (lanes_per_env == 0) lanes_per_env = 1;
-  if (lanes_per_env != 1 && lanes_per_env != 16 && lanes_per_env != 32)
-    return fail(WB_ERR_INVALID, "lanes_per_env must be 1, 16 or 32");
+  if (lanes_per_env == 0) lanes_per_env = default_lanes(env->n, env->sm_count);
+  if (!physics_lanes_supported(lanes_per_env)) return fail(WB_ERR_INVALID, "lanes_per_env must be 1, 2, 4, 8 or 16 (or 104 / 108 / 116: no leg split)");
   env->lanes = lanes_per_env;
   return WB_OK;
 }

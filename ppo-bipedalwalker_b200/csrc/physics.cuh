@@ -1,4 +1,4 @@
-// physics.cuh -- shared declarations between the physics kernels (physics.cu) and the C ABI (api.cu).
+// physics.cuh -- shared declarations between the physics kernel (physics_lanes.cu) and the C ABI (api_env.cu).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -7,8 +7,7 @@
 
 namespace wb {
 
-constexpr int kEnvsPerCta = 8;    // environments staged per CTA (one 32-byte sector per SoA row)
-constexpr int kScalarEnvsPerCta = 128;  // thread-per-environment kernel (physics_scalar.cu): environments per CTA
+constexpr int kEnvPad = 8;        // the SoA rows are padded to a multiple of 8 environments (32-byte sectors)
 constexpr int kStateFloats = WB_STATE_FLOATS;
 
 struct Material {
@@ -60,17 +59,13 @@ struct FloorConst {
   int32_t skip[4];  // axis == Vector2.Zero: skipped by AxisChecks
 };
 
-// thread-per-environment kernel (physics_scalar.cu)
-cudaError_t upload_materials_scalar(const Material* table, int count);
-cudaError_t upload_scene_constants_scalar(const float* init_state92, const FloorConst* floor);
-cudaError_t launch_physics_scalar(const PhysicsParams& p, bool trace, cudaStream_t stream);
+// host-side helpers implemented in physics_lanes.cu
+cudaError_t upload_materials(const Material* table, int count);
+cudaError_t upload_scene_constants(const float* init_state92, const FloorConst* floor);
+bool physics_lanes_supported(int lanes_per_env);
+cudaError_t launch_physics(const PhysicsParams& p, int lanes_per_env, bool trace, cudaStream_t stream);
+cudaError_t launch_rotz_debug(const float* radians, int n, int mode, float* c_out, float* s_out, cudaStream_t stream);
 cudaError_t launch_rcp_sqrt_check(uint32_t first, uint64_t count, unsigned long long* mismatches_dev, uint32_t* first_bad_dev,
                                   cudaStream_t stream);
-
-// host-side helpers implemented in physics.cu
-cudaError_t upload_materials(const Material* table, int count);
-cudaError_t upload_scene_constants(const float* init_state92, const float* floor10);
-cudaError_t launch_rotz_debug(const float* radians, int n, int mode, float* c_out, float* s_out, cudaStream_t stream);
-cudaError_t launch_physics(const PhysicsParams& p, int lanes_per_env, bool trace, cudaStream_t stream);
 
 }  // namespace wb

@@ -1,0 +1,891 @@
+// physics_lanes.cu -- lockstep rigid-body step for N independent BipedalWalker environments (sm_100a),
+// L lanes per environment (L = 1, 2, 4, 8, 16), one warp per CTA.
+//
+// Replaces, for a whole batch per launch, the reference's Environment.StepObjects and everything under it
+// (Environment.cs:126-143; Joint.cs:31-61; RigidBody.cs:54-140; Skeleton.cs:76-176; SATCollision.cs:15-104;
+// ContactPoints.cs:13-134; Impulses.cs:12-115) plus the walker glue around it (Walker.cs:49-75,132-152,
+// Environment.cs:96-122,148-154,167-180).
+//
+// The reference's step is a strictly sequential Gauss-Seidel sweep per environment (4 joints, then 5 bodies in list
+// order, every candidate pair resolved in place), so the unlimited parallelism is ACROSS environments; inside one, only
+// the 12 SAT axes of a pair and the vertices of a Move/Rotate are independent.
+//   L = 1  (throughput): every lane of a warp advances a different walker.  No redundant work, no shuffles.
+//   L > 1  (latency, few walkers per SM): the lanes of a walker first split by LEG -- during the body sweep the left leg
+//          {LLL, LLU}, the Body and the right leg {RLL, RLU} never touch each other's state (association lists,
+//          Walker.cs:204-208; the floor is immutable), so {LLL, LLU, Body} and {RLL, RLU} are swept concurrently by the two
+//          halves of the walker's lanes with bit-identical results -- and inside a half the G = L/2 lanes split the SAT axes
+//          (axis i on lane i mod G, then a lexicographic (depth, index) min over the G lanes = the reference's "first
+//          minimal axis wins") and the vertices of every Move / Rotate; the scalar parts are computed redundantly and
+//          written by lane 0 of the group.  Fewer walkers share a warp, so the warp also follows the reference's early
+//          exits more closely (a warp executes the union of its walkers' branches: with 32 walkers per warp some walker
+//          always collides).
+// State: the 92-float record is read once from the SoA arrays in HBM (coalesced), kept in shared memory as COLUMNS
+// ([slot][env]: any data-dependent access -- support vertex k, its neighbours, runtime body ids -- is conflict free and
+// lanes of one walker read by broadcast), advanced by all `iterations` substeps on chip and written back once.
+// Control flow is WARP-UNIFORM: every branch is taken on a __any_sync vote and lanes are predicated inside, so all
+// warp-level primitives use the full mask (plain SHFL / VOTE / WARPSYNC).  There are no block-level barriers.
+//
+// Arithmetic contract: IEEE binary32, every multiply/add individually rounded (never FMA; TU compiled with -fmad=false),
+// correctly rounded 1/x, sqrt and division, (float)cos/sin((double)theta) for Skeleton.Rotate -- the same operation order
+// as the reference's C# (SURVEY.md Appendix A/C).  Bit-exact against the oracle.  There is no CPU path.
+#include "physics.cuh"
+#include "physics_math.cuh"
+
+namespace wb {
+namespace pl {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__constant__ Material c_materials[WB_MAX_MATERIALS];
+__constant__ float c_init_state[kStateFloats];  // state record of a freshly created walker
+__constant__ FloorConst c_floor;
+
+enum { LLL = 0, LLU = 1, BODY = 2, RLL = 3, RLU = 4, FLOOR = 5 };
+
+// ---------------------------------------------------------------- shared-memory columns of one env
+// float2 slots: vertices body*6 + i (Body's 6th slot mirrors its vertex 0, see below), centroids, velocities
+constexpr int kV2Cen = 30;
+constexpr int kV2Vel = 35;
+constexpr int kV2Count = 40;
+// float slots
+constexpr int kFOmega = 0;
+constexpr int kFAngle = 5;
+constexpr int kFCount = 10;
+
+// The Body hull has 5 vertices; its 6th slot holds a COPY of vertex 0 that goes through the same Move/Rotate operations
+// (so it stays bit-identical to vertex 0).  Every polygon is then a 6-gon for the kernels: the duplicate never changes a
+// min/max projection, never wins the strict "first smallest" support-vertex scan, edge 4 (P5 - P4) equals the hull's closing
+// edge P0 - P4, and edge 5 (P0 - P5) is the zero vector, which SATCollision.AxisChecks itself skips (SATCollision.cs:45).
+__device__ __forceinline__ int nverts(int b) { return b == BODY ? 5 : 6; }
+
+template <int L>
+struct Env {
+  static constexpr int E = 32 / L;  // environments per warp (= per CTA)
+  float2* v2;   // this env's column of float2 slots: slot s at v2[s * E]
+  float* f;     // this env's column of float slots
+  const FloorConst* fl;  // the floor's constants (shared-memory copy: lanes index it with different runtime indices)
+  int sub;      // lane inside the env's L lanes
+  int gsub;     // lane inside the current working group (the whole env for joints, one leg's half during the body sweep)
+  int gshift;   // first lane of the current working group inside the warp
+  bool live;    // env < n
+  int flags;    // Collided bits, Terminal, floor-first (identical on the L lanes)
+  // material-derived constants (RigidBody ctor, RigidBody.cs:36-50; Impulses.cs:16-17)
+  float im_w;     // walker inverse mass
+  float ii_pole;  // 0.001f * inverse mass
+  float e_ww, mu_ww, e_wf, mu_wf;
+};
+
+template <int L> __device__ __forceinline__ float2& V2(const Env<L>& e, int slot) { return e.v2[slot * Env<L>::E]; }
+template <int L> __device__ __forceinline__ float& F1(const Env<L>& e, int slot) { return e.f[slot * Env<L>::E]; }
+template <int L> __device__ __forceinline__ float inv_inertia(const Env<L>& e, int b) { return b == BODY ? 0.0003f : e.ii_pole; }  // Walker.cs:168
+template <int L> __device__ __forceinline__ void lanes_sync() { if (L > 1) __syncwarp(); }
+// true when `pred` holds on any lane of my env's group (full-mask vote: control flow is warp-uniform)
+template <int L, int G> __device__ __forceinline__ bool group_any(const Env<L>& e, bool pred) {
+  if (L == 1) return pred;
+  const unsigned b = __ballot_sync(kFull, pred);
+  return ((b >> e.gshift) & ((1u << G) - 1u)) != 0u;
+}
+
+struct BodyDyn {
+  float2 c, v;
+  float w, im, ii;
+};
+
+template <int L> __device__ __forceinline__ BodyDyn load_dyn(const Env<L>& e, int b) {
+  BodyDyn d;
+  d.c = V2(e, kV2Cen + b);
+  d.v = V2(e, kV2Vel + b);
+  d.w = F1(e, kFOmega + b);
+  d.im = e.im_w;
+  d.ii = inv_inertia(e, b);
+  return d;
+}
+template <int L> __device__ __forceinline__ BodyDyn floor_dyn(const Env<L>& e) {
+  BodyDyn d;
+  d.c = e.fl->cen;
+  d.v = mk2(0.0f, 0.0f);
+  d.w = 0.0f;
+  d.im = 0.0f;
+  d.ii = 0.0f;
+  return d;
+}
+template <int L> __device__ __forceinline__ void store_dyn(const Env<L>& e, int b, const BodyDyn& d) {
+  V2(e, kV2Vel + b) = d.v;
+  F1(e, kFOmega + b) = d.w;
+}
+
+// Impulses.CalculateImpulse, Impulses.cs:86-115
+__device__ __forceinline__ void calculate_impulse(const BodyDyn& A, const BodyDyn& B, float2 contact, float force, float2 n,
+                                                  float2& rA, float2& rB, float& impulse) {
+  rA = vsub(contact, A.c);
+  const float2 perpA = mk2(-rA.y, rA.x);
+  const float kA = vdot(n, perpA);
+  rB = vsub(contact, B.c);
+  const float2 perpB = mk2(-rB.y, rB.x);
+  const float kB = vdot(n, perpB);
+  const float2 va = vadd(A.v, vmul(perpA, A.w));
+  const float2 vb = vadd(B.v, vmul(perpB, B.w));
+  const float2 vrel = vsub(vb, va);
+  const float vn = vdot(vrel, n);
+  const float j = fmul(-force, vn);
+  const float denom = fadd(fadd(fadd(A.im, B.im), fmul(fmul(kA, kA), A.ii)), fmul(fmul(kB, kB), B.ii));
+  impulse = fdiv(j, denom);
+}
+
+// Impulses.ApplyImpulses, Impulses.cs:57-82
+__device__ __forceinline__ void apply_impulses(BodyDyn& A, BodyDyn& B, float2 n, float impulse, float2 rA, float2 rB) {
+  const float2 J = vmul(n, impulse);
+  const float2 velA = vsub(A.v, vmul(J, A.im));
+  const float2 velB = vadd(B.v, vmul(J, B.im));
+  const float2 perpA = mk2(-rA.y, rA.x);
+  const float wA = fsub(A.w, fmul(vdot(perpA, J), A.ii));
+  const float2 perpB = mk2(-rB.y, rB.x);
+  const float wB = fadd(B.w, fmul(vdot(perpB, J), B.ii));
+  A.v = velA;
+  B.v = velB;
+  A.w = wA;
+  B.w = wB;
+}
+
+// Skeleton.Move (Skeleton.cs:76-85) of up to two bodies, split over the G lanes of the working group: items 0..5 = A's six
+// vertex slots (the Body's mirror slot moves with its vertex 0), 6 = A's centroid, 7..13 the same for B.  Predicated by `on`.
+template <int L, int G>
+__device__ __forceinline__ void move_bodies(const Env<L>& e, bool on, int A, float2 dA, bool moveB, int B, float2 dB) {
+#pragma unroll
+  for (int it0 = 0; it0 < 14; it0 += G) {
+    const int it = it0 + e.gsub;
+    const bool second = it >= 7;
+    const int k = second ? it - 7 : it;
+    const int b = second ? B : A;
+    if (on && it < 14 && (!second || moveB)) {
+      const int slot = (k < 6) ? b * 6 + k : kV2Cen + b;
+      V2(e, slot) = vadd(V2(e, slot), second ? dB : dA);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Joint.Step, Joint.cs:31-41
+template <int L, bool TRACE>
+__device__ __forceinline__ void joint_step(const Env<L>& e, int A, int ia, int B, int ib, wb_joint_trace* tr) {
+  const float2 pA = V2(e, A * 6 + ia);
+  const float2 pB = V2(e, B * 6 + ib);
+  float2 ab = vsub(pB, pA);
+  const float depth = fsqrt(fadd(fmul(ab.x, ab.x), fmul(ab.y, ab.y)));  // Vector2.Length
+  if (TRACE) {
+    if (tr && e.live && e.sub == 0) {
+      tr->active = !(depth < 0.1f);
+      tr->depth = depth;
+    }
+  }
+  const bool active = e.live && !(depth < 0.1f);
+  if (!__any_sync(kFull, active)) return;
+  ab = vnormalize_fast(ab);
+  const float2 dA = vhalf(vmul(ab, depth));
+  const float2 dB = vhalf(vmul(vneg(ab), depth));
+  BodyDyn X = load_dyn(e, B);  // Manifold(bodyA := joint._bodyB, bodyB := joint._bodyA), Joint.cs:40
+  BodyDyn Y = load_dyn(e, A);
+  lanes_sync<L>();  // every lane has read the pre-move points, centroids and velocities
+  move_bodies<L, L>(e, active, A, dA, true, B, dB);
+  X.c = vadd(X.c, dB);  // the impulse sees the POST-move centroids and joint points
+  Y.c = vadd(Y.c, dA);
+  const float2 contact = vhalf(vadd(vadd(pA, dA), vadd(pB, dB)));  // Vector2.Divide(p0 + p1, 2), Impulses.cs:35
+  float2 rX, rY;
+  float j;
+  calculate_impulse(X, Y, contact, fadd(1.0f, 1.0f), ab, rX, rY, j);
+  apply_impulses(X, Y, ab, j, rX, rY);
+  if (active && e.sub == 0) {
+    store_dyn(e, B, X);
+    store_dyn(e, A, Y);
+  }
+  lanes_sync<L>();
+}
+
+// ---------------------------------------------------------------- SAT, SATCollision.cs:15-104
+// float.MaxValue / float.MinValue seeds take part in the min/max exactly like the reference's "if (t < min) min = t"
+__device__ __forceinline__ void project6(const float2 (&P)[6], float2 ax, float& mn, float& mx) {
+  const float t0 = vdot(ax, P[0]), t1 = vdot(ax, P[1]), t2 = vdot(ax, P[2]);
+  const float t3 = vdot(ax, P[3]), t4 = vdot(ax, P[4]), t5 = vdot(ax, P[5]);
+  mn = fminf(fminf(fminf(FLT_MAX, t0), fminf(t1, t2)), fminf(fminf(t3, t4), t5));
+  mx = fmaxf(fmaxf(fmaxf(-FLT_MAX, t0), fmaxf(t1, t2)), fmaxf(fmaxf(t3, t4), t5));
+}
+__device__ __forceinline__ void project4(const float2* P, float2 ax, float& mn, float& mx) {
+  const float t0 = vdot(ax, P[0]), t1 = vdot(ax, P[1]), t2 = vdot(ax, P[2]), t3 = vdot(ax, P[3]);
+  mn = fminf(fminf(fminf(FLT_MAX, t0), t1), fminf(t2, t3));
+  mx = fmaxf(fmaxf(fmaxf(-FLT_MAX, t0), t1), fmaxf(t2, t3));
+}
+
+// ---------------------------------------------------------------- contact points, ContactPoints.cs:13-134
+struct Face {
+  float2 a, b, max;
+};
+
+// GetSignificantFace given the support vertex sv = P[k] and its neighbours (ContactPoints.cs:79-94)
+__device__ __forceinline__ Face face_from(float2 sv, float2 next, float2 prev, float2 nrm) {
+  const float2 after = vnormalize_fast(vsub(sv, next));
+  const float2 before = vnormalize_fast(vsub(sv, prev));
+  const bool use_before = vdot(nrm, before) >= vdot(nrm, after);
+  Face f;
+  f.a = use_before ? sv : next;
+  f.b = use_before ? prev : sv;
+  f.max = sv;
+  return f;
+}
+
+// GetSignificantVertex (ContactPoints.cs:97-113): first index with the strictly smallest projection
+__device__ __forceinline__ int support_index6(const float2 (&P)[6], float2 nrm) {
+  float best = FLT_MAX;
+  int k = 0;  // (k stays 0 only if no projection is below float.MaxValue: non-finite state)
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float pr = vdot(P[i], nrm);
+    const bool lt = pr < best;
+    k = lt ? i : k;
+    best = lt ? pr : best;
+  }
+  return k;
+}
+
+template <int L>
+__device__ __forceinline__ Face significant_face_body(const Env<L>& e, int b, const float2 (&P)[6], float2 nrm) {
+  const int n = nverts(b);
+  const int k = support_index6(P, nrm);
+  const int kn = (k + 1 == n) ? 0 : k + 1;
+  const int kp = (k == 0) ? n - 1 : k - 1;
+  return face_from(V2(e, b * 6 + k), V2(e, b * 6 + kn), V2(e, b * 6 + kp), nrm);
+}
+
+template <int L>
+__device__ __forceinline__ Face significant_face_floor(const Env<L>& e, float2 nrm) {
+  float best = FLT_MAX;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float pr = vdot(e.fl->v[i], nrm);
+    const bool lt = pr < best;
+    k = lt ? i : k;
+    best = lt ? pr : best;
+  }
+  return face_from(e.fl->v[k], e.fl->v[(k + 1) & 3], e.fl->v[(k + 3) & 3], nrm);
+}
+
+// ClipVectors, ContactPoints.cs:56-76: appends up to 3 points; only the first two are ever used
+__device__ __forceinline__ int clip_vectors(float2 a, float2 b, float2 nrm, float offset, float2& o0, float2& o1) {
+  int cnt = 0;
+  const float da = fsub(vdot(a, nrm), offset);
+  const float db = fsub(vdot(b, nrm), offset);
+  if (da >= 0.0f) {
+    o0 = a;
+    cnt = 1;
+  }
+  if (db >= 0.0f) {
+    if (cnt == 0) o0 = b; else o1 = b;
+    cnt++;
+  }
+  if (fmul(da, db) < 0.0f) {
+    float2 ed = vsub(b, a);
+    const float location = fdiv(da, fsub(da, db));
+    ed = vmul(ed, location);
+    ed = vadd(ed, a);
+    if (cnt == 0) o0 = ed; else if (cnt == 1) o1 = ed;
+    cnt++;
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ bool veq(float2 a, float2 b) { return a.x == b.x && a.y == b.y; }
+
+// GetContactPoints after the two significant faces are known, ContactPoints.cs:13-53
+__device__ __forceinline__ int contact_points(Face ref, Face inc, float2 normal, float2& c0, float2& c1) {
+  float2 rf = vsub(ref.b, ref.a);
+  const float2 ifv = vsub(inc.b, inc.a);
+  if (fabsf(vdot(rf, normal)) > fabsf(vdot(ifv, normal))) {
+    const Face t = ref;
+    ref = inc;
+    inc = t;
+    rf = vsub(ref.b, ref.a);
+  }
+  rf = vnormalize_fast(rf);
+  float offset = vdot(rf, ref.a);
+  float2 p0 = mk2(0.f, 0.f), p1 = mk2(0.f, 0.f);
+  int cnt = clip_vectors(inc.a, inc.b, rf, offset, p0, p1);
+  if (cnt < 2) return 0;
+  offset = vdot(rf, ref.b);
+  float2 q0 = mk2(0.f, 0.f), q1 = mk2(0.f, 0.f);
+  cnt = clip_vectors(p0, p1, vneg(rf), -offset, q0, q1);
+  if (cnt < 2) return 0;
+  cnt = 2;  // ClipVectors returns 3 points only if da >= 0, db >= 0 and da*db < 0 at once, which is impossible
+  const float2 rn = mk2(rf.y, -rf.x);
+  const float maximum = vdot(rn, ref.max);
+  // List.Remove(First()) then List.Remove(Last()): Remove deletes the first element EQUAL to the value
+  if (fsub(vdot(rn, q0), maximum) < 0.0f) {
+    q0 = q1;
+    cnt = 1;
+  }
+  const float2 last = (cnt == 2) ? q1 : q0;
+  if (fsub(vdot(rn, last), maximum) < 0.0f) {
+    if (cnt == 2) {
+      if (veq(q0, q1)) q0 = q1;  // removes index 0 when both points are equal (same value survives)
+      cnt = 1;
+    } else {
+      cnt = 0;
+    }
+  }
+  c0 = q0;
+  c1 = q1;
+  return cnt;
+}
+
+// Impulses.ResolveCollisions, Impulses.cs:12-28: both impulses come from the PRE-impulse velocities (:23-24), then both are applied (:26-27)
+__device__ __forceinline__ void resolve_impulses(BodyDyn& X, BodyDyn& Y, int ncp, float2 c0, float2 c1, float2 normal, float e, float mu) {
+  const float2 contact = (ncp == 2) ? vhalf(vadd(c0, c1)) : c0;
+  const float2 tangent = mk2(-normal.y, normal.x);
+  float2 rA, rB, rAf, rBf;
+  float j, jf;
+  calculate_impulse(X, Y, contact, fadd(1.0f, e), normal, rA, rB, j);
+  calculate_impulse(X, Y, contact, mu, tangent, rAf, rBf, jf);
+  apply_impulses(X, Y, normal, j, rA, rB);
+  apply_impulses(X, Y, tangent, jf, rAf, rBf);
+}
+
+__device__ __forceinline__ void aabb6(const float2 (&P)[6], float2& mn, float2& mx) {
+  mn.x = fminf(fminf(fminf(P[0].x, P[1].x), fminf(P[2].x, P[3].x)), fminf(P[4].x, P[5].x));
+  mn.y = fminf(fminf(fminf(P[0].y, P[1].y), fminf(P[2].y, P[3].y)), fminf(P[4].y, P[5].y));
+  mx.x = fmaxf(fmaxf(fmaxf(P[0].x, P[1].x), fmaxf(P[2].x, P[3].x)), fmaxf(P[4].x, P[5].x));
+  mx.y = fmaxf(fmaxf(fmaxf(P[0].y, P[1].y), fmaxf(P[2].y, P[3].y)), fmaxf(P[4].y, P[5].y));
+}
+// BoundingBox.IsColliding, Skeleton.cs:133-140
+__device__ __forceinline__ bool aabb_hit(float2 amin, float2 amax, float2 bmin, float2 bmax) {
+  return amin.x < bmax.x && amax.x > bmin.x && amin.y < bmax.y && amax.y > bmin.y;
+}
+
+// ---------------------------------------------------------------- one candidate of RigidBody.ResolveCollisions (RigidBody.cs:66-96)
+// FLOORB = false: a leg segment A against the other segment B of its own leg (both dynamic poles)
+// FLOORB = true : a walker body A against the static floor (scene constants)
+// `want`: this env takes part (candidate exists at this position of its list order).
+template <int L, int G, bool TRACE, bool FLOORB>
+__device__ __forceinline__ void resolve_pair(Env<L>& e, bool want, int A, int B, wb_pair_trace* tr) {
+  const FloorConst& fl = *e.fl;
+  float2 PA[6], PB[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) PA[i] = V2(e, A * 6 + i);
+  float2 amin, amax, bmin, bmax;
+  aabb6(PA, amin, amax);
+  if (FLOORB) {
+    bmin = fl.bb_min;
+    bmax = fl.bb_max;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; i++) PB[i] = V2(e, B * 6 + i);
+    aabb6(PB, bmin, bmax);
+  }
+  const bool hit = want && aabb_hit(amin, amax, bmin, bmax);
+  if (FLOORB && hit) e.flags |= (1 << A);  // if (body._isFloor) Collided = true  (before SAT: RigidBody.cs:75)
+  wb_pair_trace rec;
+  if (TRACE) {
+    rec.other = FLOORB ? FLOOR : B;
+    rec.aabb = hit ? 1 : 0;
+    rec.sat = 0;
+    rec.axis = -1;
+    rec.nx = rec.ny = rec.depth = 0.0f;
+    rec.ncontacts = 0;
+    rec.c0x = rec.c0y = rec.c1x = rec.c1y = 0.0f;
+  }
+  bool colliding = false;
+  if (__any_sync(kFull, hit)) {
+    // AxisChecks(A, B) then AxisChecks(B, A) (SATCollision.cs:19-29,39-59): axis i of the 12 (10 against the floor) goes to
+    // lane i mod G.  Once an axis separates, the reference returns false and nothing computed afterwards is used, so the
+    // rounds simply stop for an env as soon as any of its lanes saw a separating axis; a skipped (zero) axis has NaN
+    // projections and must not touch anything.  "tempDepth >= depth -> continue" keeps the FIRST minimal axis: each lane
+    // updates only on a strictly smaller depth (its axes come in increasing order) and the lanes are then combined by a
+    // lexicographic (depth, index) minimum.
+    const int nA = nverts(A);
+    float depth = FLT_MAX;
+    float2 normal = mk2(0.0f, 0.0f);
+    int idx = 0x7FFFFFFF;
+    bool sep = false;
+    // Projection.IsOverlapping + depth (SATCollision.cs:47-50,100-104): symmetric in the two projections.  Returns true when
+    // no env of the warp needs another axis.
+    auto accumulate = [&](bool use, float2 axis, int axis_idx, float omin, float omax, float tmin, float tmax) {
+      const float temp = fminf(fsub(tmax, omin), fsub(omax, tmin));
+      const bool overlapping = (omin < tmax) && (tmin < omax);
+      if (use && temp < depth) {
+        depth = temp;
+        normal = axis;
+        idx = axis_idx;
+      }
+      const bool separated = group_any<L, G>(e, use && !overlapping);  // (a vote: every lane takes part, no short-circuit)
+      sep = sep || separated;
+      return !__any_sync(kFull, hit && !sep);
+    };
+    // left normal of edge k of polygon `own`, zero test, Vector2.Normalize (SATCollision.cs:43-46)
+    auto edge_axis = [&](int own, int k, bool& skip) {
+      const float2 p0 = V2(e, own * 6 + k), p1 = V2(e, own * 6 + (k == 5 ? 0 : k + 1));
+      const float2 edge = vsub(p1, p0);
+      const float2 axis = mk2(-edge.y, edge.x);
+      skip = (axis.x == 0.0f) && (axis.y == 0.0f);
+      return vnormalize_fast(axis);
+    };
+    if (FLOORB) {
+      bool done = false;
+#pragma unroll 1
+      for (int r = 0; r < 6 && !done; r += G) {  // AxisChecks(A, floor): A's 6 edges
+        const int i = r + e.gsub;
+        const bool valid = i < 6;
+        bool skip;
+        const float2 axis = edge_axis(A, valid ? i : 0, skip);
+        float omin, omax, tmin, tmax;
+        project6(PA, axis, omin, omax);
+        project4(fl.v, axis, tmin, tmax);
+        done = accumulate(valid && !skip, axis, i, omin, omax, tmin, tmax);
+      }
+#pragma unroll 1
+      for (int r = 0; r < 4 && !done; r += G) {  // AxisChecks(floor, A): constant axes and constant own projection
+        const int i = r + e.gsub;
+        const bool valid = i < 4;
+        const int k = valid ? i : 0;
+        const float2 axis = fl.axis[k];
+        float tmin, tmax;
+        project6(PA, axis, tmin, tmax);
+        done = accumulate(valid && fl.skip[k] == 0, axis, nA + k, fl.pmin[k], fl.pmax[k], tmin, tmax);
+      }
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < 12; r += G) {  // AxisChecks(A, B) then AxisChecks(B, A)
+        const int i = r + e.gsub;
+        const bool valid = i < 12;
+        const bool ownA = i < 6;
+        const int k = ownA ? i : (valid ? i - 6 : 0);
+        bool skip;
+        const float2 axis = edge_axis(ownA ? A : B, k, skip);
+        float amn, amx, bmn, bmx;
+        project6(PA, axis, amn, amx);
+        project6(PB, axis, bmn, bmx);
+        if (accumulate(valid && !skip, axis, ownA ? i : nA + k, amn, amx, bmn, bmx)) break;
+      }
+    }
+    colliding = hit && !sep;
+    if (__any_sync(kFull, colliding)) {
+      if (G > 1) {
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) {
+          const float od = __shfl_xor_sync(kFull, depth, m);
+          const int oi = __shfl_xor_sync(kFull, idx, m);
+          const float ox = __shfl_xor_sync(kFull, normal.x, m);
+          const float oy = __shfl_xor_sync(kFull, normal.y, m);
+          if (od < depth || (od == depth && oi < idx)) {
+            depth = od;
+            idx = oi;
+            normal = mk2(ox, oy);
+          }
+        }
+      }
+      // orient: normal points from B towards A (SATCollision.cs:31-32, cached centroids)
+      BodyDyn X = load_dyn(e, A);
+      BodyDyn Y = FLOORB ? floor_dyn(e) : load_dyn(e, B);
+      if (vdot(vsub(Y.c, X.c), normal) > 0.0f) normal = vmul(normal, -1.0f);
+      const Face ref = significant_face_body(e, A, PA, normal);
+      const Face inc = FLOORB ? significant_face_floor(e, vneg(normal)) : significant_face_body(e, B, PB, vneg(normal));
+      float2 c0 = mk2(0.f, 0.f), c1 = mk2(0.f, 0.f);
+      const int ncp = contact_points(ref, inc, normal, c0, c1);
+      if (TRACE) {
+        if (colliding) {
+          rec.sat = 1;
+          rec.axis = idx;
+          rec.nx = normal.x;
+          rec.ny = normal.y;
+          rec.depth = depth;
+          rec.ncontacts = ncp;
+          if (ncp > 0) {
+            rec.c0x = c0.x;
+            rec.c0y = c0.y;
+          }
+          if (ncp > 1) {
+            rec.c1x = c1.x;
+            rec.c1y = c1.y;
+          }
+        }
+      }
+      // RigidBody.MoveObjects, RigidBody.cs:99-113, applied even with 0 contact points: static B -> A.Move(normal * depth),
+      // both dynamic -> A.Move(normal * depth / 2), B.Move(-normal * depth / 2)
+      const float2 dA = FLOORB ? vmul(normal, depth) : vhalf(vmul(normal, depth));
+      const float2 dB = FLOORB ? mk2(0.f, 0.f) : vhalf(vmul(vneg(normal), depth));
+      lanes_sync<L>();  // every lane has read the pre-move vertices, centroids and velocities
+      move_bodies<L, G>(e, colliding, A, dA, !FLOORB, B, dB);
+      if (ncp > 0) {  // impulses read the PRE-move velocities but the POST-move centroids
+        X.c = vadd(X.c, dA);
+        if (!FLOORB) Y.c = vadd(Y.c, dB);
+        resolve_impulses(X, Y, ncp, c0, c1, normal, FLOORB ? e.e_wf : e.e_ww, FLOORB ? e.mu_wf : e.mu_ww);
+        if (colliding && e.gsub == 0) {
+          store_dyn(e, A, X);
+          if (!FLOORB) store_dyn(e, B, Y);  // the floor is never written (inverse mass/inertia 0)
+        }
+      }
+      lanes_sync<L>();
+    }
+  }
+  if (TRACE) {
+    if (tr && want && e.gsub == 0) *tr = rec;
+  }
+}
+
+// ---------------------------------------------------------------- RigidBody.Step, RigidBody.cs:54-61,116-140
+// `on`: this lane group really steps body b (false for the right-leg half while the left-leg half steps the Body)
+template <int L, int G, bool TRACE>
+__device__ __forceinline__ void body_step(Env<L>& e, bool on, int b, float dt, wb_pair_trace* tr_base) {
+  // StepLinearVelocity: v += a * dt (gravity (0, 980), Walker.cs:45); Skeleton.Move(v * dt)
+  float2 v = V2(e, kV2Vel + b);
+  v = vadd(v, vmul(mk2(0.0f, 980.0f), dt));
+  const float2 d = vmul(v, dt);
+  // StepAngularVelocity: angle = WrapAngle(angle + w * dt); Skeleton.Rotate(w * dt)
+  const float w = F1(e, kFOmega + b);
+  const float theta = fmul(w, dt);
+  float ang = fadd(F1(e, kFAngle + b), theta);
+  const float PI_F = 3.14159274f, TAU_F = 6.28318548f;
+  if (ang > PI_F) ang = fsub(ang, TAU_F);
+  else if (ang < -PI_F) ang = fadd(ang, TAU_F);
+  float m11, m12;
+  rotz(theta, m11, m12);
+  const float m21 = -m12, m22 = m11;
+  const float2 cen = vadd(V2(e, kV2Cen + b), d);
+  lanes_sync<L>();  // all reads of the old centroid / velocity / angle are done
+#pragma unroll
+  for (int i0 = 0; i0 < 6; i0 += G) {
+    const int i = i0 + e.gsub;
+    if (i < 6 && on) {
+      // Move then Rotate (Vector2.Transform(p - centroid, R) + centroid, Skeleton.cs:93)
+      float2 p = vadd(V2(e, b * 6 + i), d);
+      p = vsub(p, cen);
+      float2 t;
+      t.x = fadd(fadd(fmul(p.x, m11), fmul(p.y, m21)), 0.0f);
+      t.y = fadd(fadd(fmul(p.x, m12), fmul(p.y, m22)), 0.0f);
+      V2(e, b * 6 + i) = vadd(t, cen);
+    }
+  }
+  if (e.gsub == 0 && on) {
+    V2(e, kV2Cen + b) = cen;
+    V2(e, kV2Vel + b) = v;
+    F1(e, kFAngle + b) = ang;
+  }
+  lanes_sync<L>();
+  // ResolveCollisions: candidates in Environment._rigidBodies order, skipping self and associated bodies (Walker.cs:204-208):
+  // a leg segment meets the other segment of its own leg and the floor; the Body only the floor.  The floor comes first in the
+  // list after the first Reset (Walker.cs:212-223).  Three uniform phases keep a warp whose environments disagree on the list
+  // order from running the pole-pole pair twice: [floor if floor-first] [leg partner] [floor if floor-last].
+  const int slot = (0x75420 >> (4 * b)) & 0xF;     // trace slot base {0,2,4,5,7}
+  const int partner = (0x34F01 >> (4 * b)) & 0xF;  // {LLU, LLL, -, RLU, RLL}
+  const bool floor_first = (e.flags & WB_FLAG_FLOOR_FIRST) != 0;
+#pragma unroll 1
+  for (int phase = 0; phase < 3; phase++) {
+    if (phase == 1) {
+      const bool want = on && b != BODY;
+      if (__any_sync(kFull, want))
+        resolve_pair<L, G, TRACE, false>(e, want, b, b == BODY ? LLL : partner, (TRACE && tr_base) ? tr_base + slot + (floor_first ? 1 : 0) : nullptr);
+    } else {
+      const bool want = on && ((b == BODY) ? (phase == 0) : ((phase == 0) == floor_first));
+      if (__any_sync(kFull, want))
+        resolve_pair<L, G, TRACE, true>(e, want, b, FLOOR, (TRACE && tr_base) ? tr_base + slot + ((b == BODY || floor_first) ? 0 : 1) : nullptr);
+    }
+  }
+}
+
+// Walker.GetState, Walker.cs:132-152
+template <int L>
+__device__ __forceinline__ void store_observation(const Env<L>& e, float* dst) {  // dst is 16-byte aligned (48 B per env)
+  const float2 j0 = V2(e, BODY * 6 + 1), j2 = V2(e, LLU * 6 + 2), j3 = V2(e, RLU * 6 + 2), bv = V2(e, kV2Vel + BODY);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  d4[0] = make_float4(fdiv(j0.x, 900.0f), fdiv(j0.y, 500.0f), fdiv(j2.x, 900.0f), fdiv(j2.y, 500.0f));
+  d4[1] = make_float4(fdiv(j3.x, 900.0f), fdiv(j3.y, 500.0f), fdiv(bv.x, 60.0f), fdiv(bv.y, 60.0f));
+  d4[2] = make_float4(F1(e, kFAngle + LLL), F1(e, kFAngle + LLU), F1(e, kFAngle + RLL), F1(e, kFAngle + RLU));
+}
+
+// canonical record index f < 88 (walker_b200.h) -> word index inside a column set of E environments (env column 0);
+// rows 88..91 (joint torques) stay in HBM.  The float2 slots come first, then the float slots.
+template <int L>
+__device__ __forceinline__ int record_word(int f) {
+  constexpr int E = 32 / L;
+  if (f < 58) {
+    const int vtx = f >> 1, slot = vtx + (vtx >= 17 ? 1 : 0);
+    return slot * E * 2 + (f & 1);
+  }
+  if (f < 78) return (kV2Cen + ((f - 58) >> 1)) * E * 2 + (f & 1);
+  return kV2Count * E * 2 + (f - 78) * E;
+}
+
+template <int L, int LEGS, bool TRACE>
+__global__ void __launch_bounds__(32, 16) physics_lanes_kernel(const PhysicsParams p) {
+  static_assert(LEGS == 1 || (LEGS == 2 && L >= 2), "the leg split needs at least two lanes per environment");
+  constexpr int E = 32 / L;
+  __shared__ __align__(16) float s_state[(kV2Count * 2 + kFCount) * E];
+  __shared__ FloorConst s_floor;
+  const int lane = threadIdx.x;
+  const int env0 = blockIdx.x * E;
+
+  // ---- stage the E records (all 32 lanes share the loads: SoA rows are contiguous over envs) and the floor constants
+  for (int w = lane; w < (int)(sizeof(FloorConst) / 4); w += 32)
+    reinterpret_cast<uint32_t*>(&s_floor)[w] = reinterpret_cast<const uint32_t*>(&c_floor)[w];
+  for (int idx = lane; idx < 88 * E; idx += 32) {
+    const int f = idx / E, c = idx % E;
+    const int env = env0 + c;
+    const float v = (env < p.n) ? p.state[(size_t)f * p.n_pad + env] : c_init_state[f];
+    s_state[record_word<L>(f) + (f < 78 ? 2 * c : c)] = v;
+  }
+  __syncwarp();
+
+  Env<L> e;
+  const int col = lane / L;
+  const int env = env0 + col;
+  e.v2 = reinterpret_cast<float2*>(s_state) + col;
+  e.f = s_state + kV2Count * E * 2 + col;
+  e.fl = &s_floor;
+  e.sub = lane % L;
+  e.gsub = e.sub;
+  e.gshift = col * L;
+  e.live = env < p.n;
+  const int envc = e.live ? env : 0;  // dead lanes shadow env 0 read-only (they never store)
+  if (e.sub == 0) V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
+  float* torque_rows = p.state + (size_t)88 * p.n_pad + envc;
+
+  e.flags = p.flags[envc];
+  int steps = p.steps[envc];
+  {
+    const Material mw = c_materials[p.walker_mat[envc]];
+    const Material mf = c_materials[p.floor_mat[envc]];
+    e.im_w = mw.inverse_mass;
+    e.ii_pole = fmul(0.001f, mw.inverse_mass);
+    e.e_ww = net_max(mw.restitution, mw.restitution);
+    e.mu_ww = net_min(mw.friction, mw.friction);
+    e.e_wf = net_max(mw.restitution, mf.restitution);
+    e.mu_wf = net_min(mw.friction, mf.friction);
+  }
+  float2 pos = mk2(p.pos[envc], p.pos[p.n_pad + envc]);
+  __syncwarp();
+
+  // Walker.Reset + CreateCreature: fresh walker record (constants computed on the host with the reference's formulas)
+  auto write_initial_record = [&](bool on) {
+    if (!__any_sync(kFull, on)) return;
+    __syncwarp();
+    if (on && e.sub == 0) {
+#pragma unroll 1
+      for (int f = 0; f < 88; f++) s_state[record_word<L>(f) + (f < 78 ? 2 * col : col)] = c_init_state[f];
+      V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
+      for (int k = 0; k < 4; k++) torque_rows[(size_t)k * p.n_pad] = c_init_state[88 + k];
+    }
+    __syncwarp();
+  };
+
+  if (p.phases & kPhaseResetMasked) {
+    const bool on = e.live && (p.reset_mask == nullptr || p.reset_mask[envc]);
+    write_initial_record(on);
+    if (on) {
+      e.flags = (p.phases & kPhaseFirstEpisode) ? 0 : WB_FLAG_FLOOR_FIRST;
+      steps = 0;
+      pos = V2(e, kV2Cen + BODY);  // InitialState -> Walker.Update
+    }
+  }
+  if (p.phases & kPhaseIncSteps) steps++;
+
+  if (p.phases & kPhaseTakeActions) {
+    // Matrix.Clip (Matrix.cs:377-405), Walker.TakeActions (Walker.cs:66-75), Joint.SetTorque (Joint.cs:56-61)
+    if (e.live && e.sub == 0) {
+      const float4 a4 = *reinterpret_cast<const float4*>(p.actions + (size_t)env * 4);
+      const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float a = act[k];
+        if (a >= 1.0f) a = 1.0f;
+        else if (a <= -1.0f) a = -1.0f;
+        const float change = fsub(a, torque_rows[(size_t)k * p.n_pad]);
+        torque_rows[(size_t)k * p.n_pad] = a;
+        const int bodyB = (k == 0) ? LLU : (k == 1) ? RLU : (k == 2) ? LLL : RLL;  // Walker.cs:182-185
+        F1(e, kFOmega + bodyB) = fadd(F1(e, kFOmega + bodyB), fmul(change, 5.0f));
+      }
+    }
+    __syncwarp();
+  }
+
+  if (p.phases & kPhaseStepObjects) {
+    const float dt = fdiv(p.dt, (float)p.iterations);  // deltaTime /= Hyperparameters.Iterations
+#pragma unroll 1
+    for (int it = 0; it < p.iterations; it++) {
+      wb_joint_trace* jt = nullptr;
+      wb_pair_trace* pt = nullptr;
+      if (TRACE) {
+        if (p.joint_trace) jt = p.joint_trace + ((size_t)envc * p.iterations + it) * 4;
+        if (p.pair_trace) pt = p.pair_trace + ((size_t)envc * p.iterations + it) * WB_PAIR_SLOTS;  // all 9 slots are written every substep
+      }
+      // joints in creation order (Walker.cs:182-187): (Body v1, LLU v4) (Body v1, RLU v4) (LLU v2, LLL v3) (RLU v2, RLL v3)
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) {
+        const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
+        joint_step<L, TRACE>(e, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, jt ? jt + k : nullptr);
+      }
+      // bodies in list order; the static floor's Update is a no-op (a = v = 0, returns before rotation/collisions)
+      if (LEGS == 1) {
+#pragma unroll 1
+        for (int b = 0; b < 5; b++) body_step<L, L, TRACE>(e, e.live, b, dt, pt);
+      } else {
+        // {LLL, LLU, Body} on the first half of the env's lanes, {RLL, RLU} on the second: the three subsystems share no
+        // mutable state during the sweep, so any interleaving reproduces the sequential list-order result bit for bit
+        constexpr int G = L / LEGS;
+        const int leg = e.sub / G;
+        e.gsub = e.sub % G;
+        e.gshift = col * L + leg * G;
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+          const bool on = e.live && (leg == 0 || k < 2);
+          body_step<L, G, TRACE>(e, on, leg == 0 ? k : (k < 2 ? RLL + k : RLU), dt, pt);
+        }
+        e.gsub = e.sub;
+        e.gshift = col * L;
+      }
+    }
+    if (LEGS == 2) e.flags |= __shfl_xor_sync(kFull, e.flags, L / LEGS);  // each half latched its own bodies' Collided bits
+  }
+
+  if (p.phases & kPhaseObserve) {
+    // Walker.Update, Walker.cs:49-54
+    const float2 prev = pos;
+    pos = V2(e, kV2Cen + BODY);
+    if (e.flags & ((1 << BODY) | (1 << LLU) | (1 << RLU))) e.flags |= WB_FLAG_TERMINAL;
+    // CalculateReward, Environment.cs:148-154 (incl. the "-= -0.1f" sign quirk)
+    const float dx = fsub(pos.x, prev.x);
+    const float h = fdiv(V2(e, BODY * 6 + 1).y, 500.0f);
+    float r = 0.0f;
+    r = fadd(r, (dx > 0.0f && h < 1.6f) ? dx : 0.0f);
+    r = fsub(r, (h > 1.65f) ? -0.1f : 0.0f);
+    bool terminal = false;
+    if ((e.flags & WB_FLAG_TERMINAL) || steps > p.max_timesteps) {  // Environment.cs:106-110
+      if (e.flags & WB_FLAG_TERMINAL) r = fsub(r, 40.0f);
+      terminal = true;
+    }
+    if (pos.x > 900.0f) {  // :113-117
+      r = fadd(r, 80.0f);
+      terminal = true;
+    }
+    const bool reset_now = e.live && terminal && (p.phases & kPhaseAutoReset);
+    write_initial_record(reset_now);
+    if (reset_now) {
+      e.flags = WB_FLAG_FLOOR_FIRST;
+      steps = 0;
+      pos = V2(e, kV2Cen + BODY);
+    }
+    if (e.live && e.sub == 0) {
+      store_observation(e, p.obs + (size_t)env * WB_OBS);
+      p.reward[env] = r;
+      p.done[env] = terminal ? 1 : 0;
+    }
+  } else if (p.phases & kPhaseObsOnly) {
+    if (e.live && e.sub == 0) store_observation(e, p.obs + (size_t)env * WB_OBS);
+  }
+
+  if (e.live && e.sub == 0) {
+    p.flags[env] = e.flags;
+    p.steps[env] = steps;
+    p.pos[env] = pos.x;
+    p.pos[p.n_pad + env] = pos.y;
+  }
+  __syncwarp();
+  // ---- write the records back (same coalesced pattern)
+  for (int idx = lane; idx < 88 * E; idx += 32) {
+    const int f = idx / E, c = idx % E;
+    if (env0 + c < p.n) p.state[(size_t)f * p.n_pad + env0 + c] = s_state[record_word<L>(f) + (f < 78 ? 2 * c : c)];
+  }
+}
+
+// test hook: compares rcp_sqrt_rn(s) with __frcp_rn(__fsqrt_rn(s)) for every bit pattern in [first, first + count)
+__global__ void rcp_sqrt_check_kernel(uint32_t first, uint64_t count, unsigned long long* mismatches, uint32_t* first_bad) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint32_t bits = first + (uint32_t)i;
+    const float s = __uint_as_float(bits);
+    const uint32_t a = __float_as_uint(rcp_sqrt_rn(s));
+    const uint32_t b = __float_as_uint(__frcp_rn(__fsqrt_rn(s)));
+    const bool both_nan = ((a & 0x7FFFFFFFu) > 0x7F800000u) && ((b & 0x7FFFFFFFu) > 0x7F800000u);
+    if (a != b && !both_nan) {
+      bad++;
+      atomicMin(first_bad, bits);
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+// test hook: evaluates the rotation coefficients for an array of angles (mode 0: production path, 1: force the
+// double-double slow path, 2: force the libm-style sincos path)
+__global__ void rotz_debug_kernel(const float* radians, int n, int mode, float* c_out, float* s_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float c, s;
+  if (mode == 1) {
+    sincos_dd_small((double)radians[i], c, s);
+  } else if (mode == 2) {
+    double sd, cd;
+    sincos((double)radians[i], &sd, &cd);
+    c = (float)cd;
+    s = (float)sd;
+  } else {
+    rotz(radians[i], c, s);
+  }
+  c_out[i] = c;
+  s_out[i] = s;
+}
+
+template <int L, int LEGS>
+static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t stream) {
+  constexpr int E = 32 / L;
+  const int grid = (p.n + E - 1) / E;
+  if (trace)
+    physics_lanes_kernel<L, LEGS, true><<<grid, 32, 0, stream>>>(p);
+  else
+    physics_lanes_kernel<L, LEGS, false><<<grid, 32, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pl
+
+// ---------------------------------------------------------------- host side
+cudaError_t upload_materials(const Material* table, int count) {
+  return cudaMemcpyToSymbol(pl::c_materials, table, sizeof(Material) * count);
+}
+
+cudaError_t upload_scene_constants(const float* init_state92, const FloorConst* floor) {
+  cudaError_t e = cudaMemcpyToSymbol(pl::c_init_state, init_state92, sizeof(float) * kStateFloats);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(pl::c_floor, floor, sizeof(FloorConst));
+}
+
+// variant code = lanes per environment (1, 2, 4, 8, 16; for >= 2 the lanes split by leg first), or 100 + lanes (4, 8, 16) for
+// the measured-for-comparison layout without the leg split (all lanes of a walker work on one pair)
+bool physics_lanes_supported(int variant) {
+  switch (variant) {
+    case 1: case 2: case 4: case 8: case 16: case 104: case 108: case 116: return true;
+    default: return false;
+  }
+}
+
+cudaError_t launch_physics(const PhysicsParams& p, int variant, bool trace, cudaStream_t stream) {
+  switch (variant) {
+    case 1: return pl::launch_l<1, 1>(p, trace, stream);
+    case 2: return pl::launch_l<2, 2>(p, trace, stream);
+    case 4: return pl::launch_l<4, 2>(p, trace, stream);
+    case 8: return pl::launch_l<8, 2>(p, trace, stream);
+    case 16: return pl::launch_l<16, 2>(p, trace, stream);
+    case 104: return pl::launch_l<4, 1>(p, trace, stream);
+    case 108: return pl::launch_l<8, 1>(p, trace, stream);
+    case 116: return pl::launch_l<16, 1>(p, trace, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_rcp_sqrt_check(uint32_t first, uint64_t count, unsigned long long* mismatches_dev, uint32_t* first_bad_dev,
+                                  cudaStream_t stream) {
+  pl::rcp_sqrt_check_kernel<<<148 * 8, 256, 0, stream>>>(first, count, mismatches_dev, first_bad_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rotz_debug(const float* radians, int n, int mode, float* c_out, float* s_out, cudaStream_t stream) {
+  pl::rotz_debug_kernel<<<(n + 255) / 256, 256, 0, stream>>>(radians, n, mode, c_out, s_out);
+  return cudaGetLastError();
+}
+
+}  // namespace wb

@@ -12,14 +12,15 @@ wb = ge.load_package(); wb.init(0)
 env = wb.EnvBatch(n, floor_materials="Wood")
 if lanes: env.set_variant(lanes)
 rng = np.random.default_rng(0)
-a = torch.from_numpy(rng.uniform(-1, 1, (n, 4)).astype(np.float32)).cuda()
+warm = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+acts = [torch.from_numpy(rng.uniform(-1, 1, (n, 4)).astype(np.float32)).cuda() for _ in range(8)]  # fresh actions every step
 obs = torch.empty(n, 12, device="cuda"); rew = torch.empty(n, device="cuda"); done = torch.empty(n, dtype=torch.uint8, device="cuda")
 env.set_stream(torch.cuda.current_stream().cuda_stream)
-for _ in range(3): env.step_dev(a, obs, rew, done)
+for i in range(warm): env.step_dev(acts[i % 8], obs, rew, done)
 torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(K): env.step_dev(a, obs, rew, done)
+for i in range(K): env.step_dev(acts[i % 8], obs, rew, done)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print(f"n={n} lanes={lanes or 1} {ms:.3f} ms/step  {n/ms*1e3:.3e} env-steps/s  done_frac={done.float().mean().item():.3f}")
+print(f"n={n} lanes={lanes or "auto"} {ms:.3f} ms/step  {n/ms*1e3:.3e} env-steps/s  done_frac={done.float().mean().item():.3f}")
