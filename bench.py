@@ -9,8 +9,13 @@ env-step (seeded, generated once), dt = 0x1.111134p-6, Iterations = 50, auto-res
 env-step kernel over all walkers of the rank.  Multi-GPU: environments are block-sharded, no data-path collective
 (weak scaling, 4096 walkers per GPU).
 
+Both arms first run PREROLL (64) untimed env-steps so that the walkers are in a mixed, decorrelated state (right after
+construction all walkers are identical, which flatters a SIMT kernel: no divergence).
+
 Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps an L2 flush (256 MiB
 memset) runs OUTSIDE the event pairs; ms_per_step = sum of the K event intervals / K, max over ranks.
+Extra keys: "at_scale" = the same step on 262144 walkers per GPU (device-resident, the throughput regime the north-star
+target is phrased in); "secondary" = PPO samples/s (configs[2]).
 """
 from __future__ import annotations
 
@@ -29,6 +34,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 N_ENVS_PER_GPU = 4096
+N_ENVS_AT_SCALE = 262144   # "at_scale": the same step with the GPU full (one lane per walker)
+PREROLL = 64               # untimed env-steps before the warm-up: the batch leaves the synchronized spawn transient
 SEED = 1234
 BYTES_PER_ENV_STEP = 2 * 376 + 16 + 56   # read state + actions, write state + obs/reward/done = 824 B
 BYTES_PER_SUBSTEP = 2 * 376              # if the state round-tripped HBM every substep (it does not: 50 substeps are fused)
@@ -105,7 +112,8 @@ def cpu_baseline(O, budget_s=12.0, max_steps=4000, nthreads=0):
     n = N_ENVS_PER_GPU
     env = O.EnvBatch(n, floor="Wood")
     acts = make_actions(n, 8, 0)
-    env.step(acts[0], nthreads=nthreads)  # warm-up
+    for k in range(PREROLL):
+        env.step(acts[k % 8], nthreads=nthreads)  # pre-roll + warm-up
     t0 = time.perf_counter()
     k = 0
     while k < max_steps and (time.perf_counter() - t0) < budget_s:
@@ -126,12 +134,12 @@ def run_reference(args):
     O = ge.load_oracle()
     n = N_ENVS_PER_GPU
     env = O.EnvBatch(n, floor="Wood")
-    acts = make_actions(n, args.warmup + args.steps, 0)
-    for w in range(args.warmup):
+    acts = make_actions(n, PREROLL + args.warmup + args.steps, 0)
+    for w in range(PREROLL + args.warmup):
         env.step(acts[w])
     t0 = time.perf_counter()
     for k in range(args.steps):
-        env.step(acts[args.warmup + k])
+        env.step(acts[PREROLL + args.warmup + k])
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     cores = os.cpu_count() or 1
@@ -152,7 +160,7 @@ def workload_config(n_gpus, cpu=False):
     return {"workload": f"{N_ENVS_PER_GPU} lockstep walkers per {'host' if cpu else 'GPU'}, physics step only, Wood ground, random actions "
                         "(BASELINE.json configs[1])",
             "walkers_per_gpu": N_ENVS_PER_GPU, "iterations": 50, "dt": "0x1.111134p-6", "floor": "Wood", "walker": "Carpet",
-            "actions": f"U(-1,1) numpy PCG64 seed [{SEED}, rank]", "auto_reset": True,
+            "actions": f"U(-1,1) numpy PCG64 seed [{SEED}, rank]", "auto_reset": True, "preroll_env_steps": PREROLL,
             "parallelism": f"env-shard x{n_gpus}, no data-path collective",
             "l2": "256 MiB memset between timed steps, outside the event pairs"}
 
@@ -202,8 +210,8 @@ def bench_ppo(wb, torch, stream, steps, warmup, flush):
             "ms_per_step": ms, "steps": steps, "dtype": "f32", "config": {"workload": "65536-sample minibatch, synthetic obs (BASELINE.json configs[2])"},
             "gpu_launches": agent.launch_count() - l0,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops,
-                         "traffic": ncu_traffic("ppo_fused_kernel"),
-                         "note": f"32640 flop/sample; fp32 CUDA-core kernel this round (no tensor-pipe use yet); peak = {which} dense bf16"}}
+                         "traffic": ncu_traffic("ppo_tc_kernel"),
+                         "note": f"32640 flop/sample; peak = {which} dense bf16 (the kernel computes in fp32 accuracy: 3xTF32 on tcgen05)"}}
 
 
 def run_ours(args):
@@ -222,7 +230,9 @@ def run_ours(args):
     n = N_ENVS_PER_GPU
     K, W = args.steps, args.warmup
     env = wb.EnvBatch(n, floor_materials="Wood", stream=stream)
-    acts_host = make_actions(n, W + K, rank)
+    acts_all = make_actions(n, PREROLL + W + K, rank)
+    acts_pre, acts_host = acts_all[:PREROLL], acts_all[PREROLL:]
+    acts_pre_dev = torch.from_numpy(acts_pre).cuda()
     acts_dev = torch.from_numpy(acts_host).cuda()
     obs_d = torch.empty(n, 12, device="cuda")
     rew_d = torch.empty(n, device="cuda")
@@ -238,6 +248,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
+    for w in range(PREROLL):
+        env.step_dev(acts_pre_dev[w], obs_d, rew_d, done_d)
     for w in range(W):
         env.step_dev(acts_dev[w], obs_d, rew_d, done_d)
     barrier()
@@ -264,6 +276,8 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host actions in, host obs/reward/done out, every step
     env2 = wb.EnvBatch(n, floor_materials="Wood", stream=stream)
+    for w in range(PREROLL):
+        env2.step_dev(acts_pre_dev[w], obs_d, rew_d, done_d)
     acts_pin = torch.from_numpy(acts_host).pin_memory()
     obs_h = torch.empty(n, 12).pin_memory()
     rew_h = torch.empty(n).pin_memory()
@@ -286,6 +300,42 @@ def run_ours(args):
     e2e_ms_step = float(t2.item()) / K
     clocks = sampler.stop() if sampler else None
 
+    # ---- the same step with the GPU full: 262144 walkers per GPU, one lane per walker (device-resident)
+    del env2
+    na = N_ENVS_AT_SCALE
+    env3 = wb.EnvBatch(na, floor_materials="Wood", stream=stream)
+    rng = np.random.default_rng([SEED, rank, 7])
+    acts3 = torch.from_numpy(rng.uniform(-1.0, 1.0, (8, na, 4)).astype(np.float32)).cuda()
+    obs3 = torch.empty(na, 12, device="cuda")
+    rew3 = torch.empty(na, device="cuda")
+    done3 = torch.empty(na, dtype=torch.uint8, device="cuda")
+    for w in range(PREROLL + 3):
+        env3.step_dev(acts3[w % 8], obs3, rew3, done3)
+    barrier()
+    ka = max(3, min(K, 10))
+    tot3 = 0.0
+    for k in range(ka):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env3.step_dev(acts3[k % 8], obs3, rew3, done3)
+        e1.record()
+        e1.synchronize()
+        tot3 += e0.elapsed_time(e1)
+    barrier()
+    t3 = torch.tensor([tot3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    ms3 = float(t3.item()) / ka
+    hbm_peak = measured_peaks()[0]
+    at_scale = {"value": world * na / (ms3 * 1e-3), "unit": "env-steps/s", "walkers_per_gpu": na, "ms_per_step": ms3, "steps": ka,
+                "lanes_per_walker": env3.get_variant(),
+                "roofline": {"bound": "hbm", "achieved": na * BYTES_PER_ENV_STEP / (ms3 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": na * BYTES_PER_ENV_STEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
+                             "substep_granular_frac": na * 50 * BYTES_PER_SUBSTEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": ncu_traffic("physics_lanes_kernel_262144")}}
+    del env3
+
     if rank == 0:
         hbm, tflops, which = measured_peaks()
         achieved = n * BYTES_PER_ENV_STEP / (kernel_ms_local * 1e-3) / 1e9
@@ -298,7 +348,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": n * (48 + 4 + 1), "ms_per_step": e2e_ms_step},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": ncu_traffic("physics_step_kernel"),
+                         "traffic": ncu_traffic("physics_lanes_kernel_4096"),
+                         "kernel": f"physics_lanes_kernel, {env.get_variant()} lanes per walker",
                          "note": f"824 B/env-step x {n} walkers per launch / CUDA-event launch time; peak = {which} copy bandwidth. "
                                  "The 50 substeps are fused on chip, so the kernel is issue/latency-bound, not HBM-bound",
                          "substep_granular": {"achieved": achieved_sub, "frac": achieved_sub / hbm,
@@ -306,6 +357,7 @@ def run_ours(args):
             "clocks": clocks,
             "episodes_finished_in_timed_region": ndone,
         }
+        line["at_scale"] = at_scale
         if world == 1:
             O = ge.load_oracle()
             line["cpu_baseline"], _ = cpu_baseline(O)

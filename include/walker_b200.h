@@ -143,6 +143,7 @@ int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out);
 /* lanes per environment of the physics kernel: 1 (one thread per walker: throughput, large batches), 2, 4, 8 or 16 (the lanes of
  * a walker split its SAT axes and vertices: latency, small batches); 0 = chosen from the batch size (the default) */
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env);
+int32_t wb_env_get_variant(const wb_env_batch* env, int32_t* lanes_per_env_out);
 
 /* test hook: the rotation coefficients (float)Math.Cos((double)r), (float)Math.Sin((double)r) of Matrix.CreateRotationZ as used by
  * Skeleton.Rotate (Skeleton.cs:93). mode 0: production path, 1: forced double-double path, 2: forced device sincos path */

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         "wb_env_step_dev": (C.c_int32, [vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
         "wb_env_launch_count": (C.c_int32, [vp, i64p]),
         "wb_env_set_variant": (C.c_int32, [vp, C.c_int32]),
+        "wb_env_get_variant": (C.c_int32, [vp, ip]),
         "wb_debug_rotz": (C.c_int32, [C.c_int32, vp, C.c_int32, vp, vp]),
         "wb_debug_rcp_sqrt_check": (C.c_int32, [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
         "wb_policy_create": (C.c_int32, [C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, hpp, C.POINTER(vp)]),

@@ -379,6 +379,12 @@ int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env) {
   return WB_OK;
 }
 
+int32_t wb_env_get_variant(const wb_env_batch* env, int32_t* lanes_per_env_out) {
+  WB_REQUIRE(env && lanes_per_env_out, "null argument");
+  *lanes_per_env_out = env->lanes;
+  return WB_OK;
+}
+
 int32_t wb_env_reset(wb_env_batch* env, const uint8_t* mask_host, int32_t first_episode) {
   WB_REQUIRE(env, "env is null");
   const uint8_t* d_mask = nullptr;

@@ -106,6 +106,12 @@ class EnvBatch:
     def set_variant(self, lanes_per_env: int):
         check(lib().wb_env_set_variant(self._h, lanes_per_env))
 
+    def get_variant(self) -> int:
+        """Lanes per environment of the physics kernel in use (chosen from the batch size unless set_variant was called)."""
+        v = C.c_int32(0)
+        check(lib().wb_env_get_variant(self._h, C.byref(v)))
+        return int(v.value)
+
     def sync(self):
         check(lib().wb_env_sync(self._h))
 
