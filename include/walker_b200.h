@@ -191,6 +191,19 @@ int32_t wb_policy_sample_dev(wb_policy* p, int32_t n, const float* states_dev, c
 int32_t wb_policy_sample_philox_dev(wb_policy* p, int32_t n, const float* states_dev, uint64_t seed, uint64_t step,
                                     float* actions_dev, float* logp_dev, float* mean_dev);
 
+/* one policy step of a lockstep rollout, all on the device: SampleActions (Philox stream (seed, step)) and the critic's value
+ * estimate (PPOAgent.GetValueEstimate, PPOAgent.cs:350-364) in ONE launch; mean_dev / value_dev may be NULL */
+int32_t wb_policy_act_dev(wb_policy* p, int32_t n, const float* states_dev, uint64_t seed, uint64_t step, float* actions_dev,
+                          float* logp_dev, float* mean_dev, float* value_dev);
+/* rollout -> update glue for N lockstep environments (PPOAgent.cs:414-498 applied per episode fragment): time-major buffers
+ * [horizon][n_envs]; done != 0 marks the last step of an episode; the segment end truncates like a trajectory end */
+int32_t wb_segment_returns_dev(wb_policy* p, int32_t n_envs, int32_t horizon, const float* rewards_dev, const float* values_dev,
+                               const uint8_t* dones_dev, float* returns_dev, float* advantages_dev);
+/* PPOAgent.CreateBatches (PPOAgent.cs:501-540): gather rows index_dev[0..batch) of the rollout pool into a contiguous minibatch */
+int32_t wb_gather_minibatch_dev(wb_policy* p, int32_t batch, const int32_t* index_dev, const float* states_pool, const float* actions_pool,
+                                const float* logp_pool, const float* advantages_pool, const float* returns_pool, float* states_out,
+                                float* actions_out, float* logp_out, float* advantages_out, float* returns_out);
+
 /* PPOAgent.Train(Batch) gradient part (PPOAgent.cs:218-342): Zero(), then for every sample the
  * clipped-surrogate dL/dmu and 2(V-G)/B, back-propagated and accumulated; gradients stay on the device
  * (wb_policy_get_grads).  n = samples in this call (this rank's shard); hp.batch_size is the divisor B.

@@ -263,6 +263,48 @@ int32_t wb_policy_sample_philox_dev(wb_policy* p, int32_t n, const float* states
   return WB_OK;
 }
 
+int32_t wb_policy_act_dev(wb_policy* p, int32_t n, const float* states_dev, uint64_t seed, uint64_t step, float* actions_dev,
+                          float* logp_dev, float* mean_dev, float* value_dev) {
+  WB_REQUIRE(p && states_dev && actions_dev && logp_dev, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  MlpParams m;
+  fill_mlp_common(p, m, n, kModeSamplePhilox);
+  m.states = states_dev;
+  m.seed = seed;
+  m.step = step;
+  m.out_actions = actions_dev;
+  m.out_logp = logp_dev;
+  m.mean = mean_dev;
+  m.value = value_dev;
+  WB_CUDA(run_mlp(p, m));
+  p->launches++;
+  return WB_OK;
+}
+
+int32_t wb_segment_returns_dev(wb_policy* p, int32_t n_envs, int32_t horizon, const float* rewards_dev, const float* values_dev,
+                               const uint8_t* dones_dev, float* returns_dev, float* advantages_dev) {
+  WB_REQUIRE(p && rewards_dev && values_dev && dones_dev && returns_dev && advantages_dev, "null argument");
+  WB_REQUIRE(n_envs > 0 && horizon > 0, "n_envs and horizon must be positive");
+  if (p->hp.normalize_advantages)
+    return fail(WB_ERR_UNSUPPORTED, "NormalizeAdvantages is per trajectory in the reference (PPOAgent.cs:461-472); the segment form does not define it");
+  WB_CUDA(launch_segment_returns(rewards_dev, values_dev, dones_dev, n_envs, horizon, p->hp.gamma, p->hp.lambda, p->hp.use_gae,
+                                 returns_dev, advantages_dev, p->stream));
+  p->launches++;
+  return WB_OK;
+}
+
+int32_t wb_gather_minibatch_dev(wb_policy* p, int32_t batch, const int32_t* index_dev, const float* states_pool, const float* actions_pool,
+                                const float* logp_pool, const float* advantages_pool, const float* returns_pool, float* states_out,
+                                float* actions_out, float* logp_out, float* advantages_out, float* returns_out) {
+  WB_REQUIRE(p && index_dev && states_pool && actions_pool && logp_pool && advantages_pool && returns_pool, "null argument");
+  WB_REQUIRE(states_out && actions_out && logp_out && advantages_out && returns_out, "null argument");
+  WB_REQUIRE(batch > 0, "batch must be positive");
+  WB_CUDA(launch_gather_minibatch(index_dev, batch, states_pool, actions_pool, logp_pool, advantages_pool, returns_pool, states_out,
+                                  actions_out, logp_out, advantages_out, returns_out, p->stream));
+  p->launches++;
+  return WB_OK;
+}
+
 int32_t wb_policy_sample(wb_policy* p, int32_t n, const float* states_host, const float* uniforms_host, float* actions_host,
                          float* logp_host, float* mean_host) {
   WB_REQUIRE(p && states_host && uniforms_host && actions_host && logp_host, "null argument");

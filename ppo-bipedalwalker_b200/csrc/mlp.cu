@@ -468,7 +468,75 @@ __global__ void returns_kernel(const float* rewards, const float* values, int n,
   }
 }
 
+// The same recurrences over a time-major rollout buffer [T][N] of N lockstep environments (the reference trains on one
+// episode of one environment, PPOAgent.cs:147; here every environment contributes the fragments of its episodes that fall
+// inside the T-step segment).  One thread per environment, reverse scan; a step with done != 0 is the LAST step of its
+// episode, so the recurrence restarts there exactly like at the end of a trajectory (next return / next value = 0), and the
+// segment end is treated the same way (truncation).
+__global__ void segment_returns_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
+                                       int n_envs, int T, float gamma, float lambda, int use_gae, float* __restrict__ returns,
+                                       float* __restrict__ advantages) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  if (use_gae) {
+    const float next_gae = 0.0f;  // never updated in the reference (PPOAgent.cs:414-444)
+    float next_value = 0.0f;
+    for (int t = T - 1; t >= 0; t--) {
+      const size_t i = (size_t)t * n_envs + e;
+      if (dones[i]) next_value = 0.0f;
+      const float cur = values[i];
+      const float delta = __fsub_rn(__fadd_rn(rewards[i], __fmul_rn(gamma, next_value)), cur);
+      next_value = cur;
+      const float gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma, lambda), next_gae));
+      advantages[i] = gae;
+      returns[i] = __fadd_rn(gae, cur);
+    }
+  } else {
+    float g = 0.0f;
+    for (int t = T - 1; t >= 0; t--) {
+      const size_t i = (size_t)t * n_envs + e;
+      if (dones[i]) g = 0.0f;
+      g = __fadd_rn(rewards[i], __fmul_rn(g, gamma));
+      returns[i] = g;
+      advantages[i] = __fsub_rn(g, values[i]);
+    }
+  }
+}
+
+// PPOAgent.CreateBatches (PPOAgent.cs:501-540) on the device: rows index[b] of the rollout pool -> a contiguous minibatch.
+// 22 floats per sample: state 12, action 4, log-probability 4, advantage, return; one thread per (sample, float).
+__global__ void gather_minibatch_kernel(const int32_t* __restrict__ index, int B, const float* __restrict__ states,
+                                        const float* __restrict__ actions, const float* __restrict__ logp, const float* __restrict__ adv,
+                                        const float* __restrict__ ret, float* __restrict__ o_states, float* __restrict__ o_actions,
+                                        float* __restrict__ o_logp, float* __restrict__ o_adv, float* __restrict__ o_ret) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / 22, f = gid % 22;
+  if (b >= B) return;
+  const size_t src = (size_t)index[b];
+  if (f < 12) o_states[(size_t)b * 12 + f] = states[src * 12 + f];
+  else if (f < 16) o_actions[(size_t)b * 4 + (f - 12)] = actions[src * 4 + (f - 12)];
+  else if (f < 20) o_logp[(size_t)b * 4 + (f - 16)] = logp[src * 4 + (f - 16)];
+  else if (f == 20) o_adv[b] = adv[src];
+  else o_ret[b] = ret[src];
+}
+
 // ---------------------------------------------------------------- host side
+cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, int n_envs, int T, float gamma,
+                                   float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream) {
+  segment_returns_kernel<<<(n_envs + 127) / 128, 128, 0, stream>>>(rewards, values, dones, n_envs, T, gamma, lambda, use_gae, returns,
+                                                                   advantages);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_minibatch(const int32_t* index, int B, const float* states, const float* actions, const float* logp,
+                                    const float* adv, const float* ret, float* o_states, float* o_actions, float* o_logp, float* o_adv,
+                                    float* o_ret, cudaStream_t stream) {
+  const long total = (long)B * 22;
+  gather_minibatch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(index, B, states, actions, logp, adv, ret, o_states,
+                                                                               o_actions, o_logp, o_adv, o_ret);
+  return cudaGetLastError();
+}
+
 int mlp_grid_for(int n, int sm_count) {
   const int ntiles = (n + kTile - 1) / kTile;
   return ntiles < sm_count ? (ntiles > 0 ? ntiles : 1) : sm_count;

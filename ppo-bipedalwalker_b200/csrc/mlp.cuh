@@ -75,6 +75,12 @@ cudaError_t launch_adam(const AdamParams& p, cudaStream_t stream);
 cudaError_t launch_returns(const float* rewards, const float* values, int n, float gamma, float lambda, int use_gae, int normalize,
                            float norm_eps, float* returns, float* advantages, cudaStream_t stream);
 
+cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, int n_envs, int T, float gamma,
+                                   float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream);
+cudaError_t launch_gather_minibatch(const int32_t* index, int B, const float* states, const float* actions, const float* logp,
+                                    const float* adv, const float* ret, float* o_states, float* o_actions, float* o_logp, float* o_adv,
+                                    float* o_ret, cudaStream_t stream);
+
 int tc_grid_for(int n, int sm_count);
 cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M, int N, int K, int a_mn, int b_mn, int passes,

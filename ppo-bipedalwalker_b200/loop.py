@@ -1,0 +1,133 @@
+"""Lockstep PPO loop over N walkers, everything resident on the GPU(s) (BASELINE.json configs[3]).
+
+What the reference does for ONE walker per episode -- Environment.Update (Environment.cs:64-92): record state, SampleActions,
+TakeActions(Clip(a)), Step, record action / log-probability / reward, and at the end PPOAgent.Train (PPOAgent.cs:147-172):
+values, returns, advantages, Epochs x shuffled mini-batches of Train(Batch) -- runs here for N walkers at once:
+
+  rollout   `horizon` env-steps; per env-step TWO kernel launches: wb_policy_act_dev (actor + critic + Philox Box-Muller sampling +
+            log-probabilities) and wb_env_step_dev (the fused physics step with auto-reset).  The trajectory (states, UNCLIPPED
+            actions and their log-probabilities -- Environment.cs:87-88 --, rewards, dones, values) stays in HBM, time-major.
+  update    wb_segment_returns_dev (MC return / the reference's GAE per episode fragment), then `epochs` x (pool / minibatch)
+            mini-batches: index permutation (sampling without replacement, remainder dropped, PPOAgent.cs:501-540) ->
+            wb_gather_minibatch_dev -> wb_ppo_grad_dev -> all-reduce(sum) of the 6 152-float gradient buffer -> wb_adam_step.
+
+Multi-GPU (one process per GPU, torchrun): the walkers are block-sharded, rollouts never communicate; every rank draws its
+share (minibatch / world) of each global mini-batch from its OWN pool, gradients are divided by the GLOBAL batch size inside
+the kernel, so one NCCL all-reduce(sum) per mini-batch makes every rank apply the identical Adam step (weights stay
+bit-identical across ranks).  PyTorch is used for device buffers, the permutation and the collective only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import dist as _dist
+from ._lib import ACT, OBS, Hyperparams, check, lib, ptr
+from .env import DT_FRAME, EnvBatch, default_hyperparams
+from .ppo import PPOAgent
+
+
+class VectorPPO:
+    def __init__(self, n_envs_global: int, horizon: int = 64, minibatch_global: int = 65536, epochs: int = 1,
+                 floor="Metal", walker="Carpet", hp: Hyperparams | None = None, seed: int = 0, policy_variant: int | None = None):
+        import torch
+        self.torch = torch
+        self.rank, self.local_rank, self.world = _dist.world()
+        lo, hi = _dist.shard_range(n_envs_global, self.rank, self.world)
+        self.n = hi - lo
+        self.env_offset = lo
+        self.n_global = n_envs_global
+        self.T = horizon
+        assert minibatch_global % self.world == 0, "the global mini-batch must split evenly over the ranks"
+        self.mb_global = minibatch_global
+        self.mb_local = minibatch_global // self.world
+        self.pool_local = self.n * self.T
+        assert self.pool_local >= self.mb_local, "local rollout pool smaller than the local mini-batch share"
+        self.epochs = epochs
+        self.seed = seed
+        self.hp = hp if hp is not None else default_hyperparams()
+        self.hp.batch_size = minibatch_global  # the divisor B of every per-sample gradient (PPOAgent.cs:326,333)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.env = EnvBatch(self.n, floor_materials=floor, walker_materials=walker, hp=self.hp, stream=self.stream)
+        self.agent = PPOAgent(hp=self.hp, seed=seed, stream=self.stream)  # same seed -> identical Xavier weights on every rank
+        if policy_variant is not None:
+            self.agent.set_variant(policy_variant)
+        dev = f"cuda:{torch.cuda.current_device()}"
+        f32 = dict(device=dev, dtype=torch.float32)
+        n, T = self.n, self.T
+        self.states = torch.empty(T, n, OBS, **f32)
+        self.actions = torch.empty(T, n, ACT, **f32)
+        self.logp = torch.empty(T, n, ACT, **f32)
+        self.rewards = torch.empty(T, n, **f32)
+        self.values = torch.empty(T, n, **f32)
+        self.dones = torch.empty(T, n, device=dev, dtype=torch.uint8)
+        self.returns = torch.empty(T, n, **f32)
+        self.adv = torch.empty(T, n, **f32)
+        self.obs = torch.from_numpy(self.env.get_obs()).to(dev)  # Environment.InitialState
+        self.mb = [torch.empty(self.mb_local, OBS, **f32), torch.empty(self.mb_local, ACT, **f32), torch.empty(self.mb_local, ACT, **f32),
+                   torch.empty(self.mb_local, **f32), torch.empty(self.mb_local, **f32)]
+        self.grad_view = _dist.grad_tensor(self.agent)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed * 1000003 + self.rank)
+        self.step_counter = 0
+        self.iterations = 0
+
+    # -- rollout: `horizon` lockstep env-steps, 2 launches each
+    def rollout(self):
+        L = lib()
+        h_agent, h_env = self.agent._h, self.env._h
+        for t in range(self.T):
+            self.states[t].copy_(self.obs)
+            # distinct Philox streams per rank: the counter is (local sample index, action dim, step)
+            check(L.wb_policy_act_dev(h_agent, self.n, ptr(self.obs), self.seed * 7919 + self.rank, self.step_counter, ptr(self.actions[t]),
+                                      ptr(self.logp[t]), None, ptr(self.values[t])))
+            check(L.wb_env_step_dev(h_env, ptr(self.actions[t]), C.c_float(DT_FRAME), 1, ptr(self.obs), ptr(self.rewards[t]),
+                                    ptr(self.dones[t])))
+            self.step_counter += 1
+
+    # -- update: returns/advantages, epochs x mini-batches with one all-reduce each
+    def update(self):
+        torch = self.torch
+        L = lib()
+        h = self.agent._h
+        check(L.wb_segment_returns_dev(h, self.n, self.T, ptr(self.rewards), ptr(self.values), ptr(self.dones), ptr(self.returns),
+                                       ptr(self.adv)))
+        S, A, LP = self.states.view(-1, OBS), self.actions.view(-1, ACT), self.logp.view(-1, ACT)
+        ADV, RET = self.adv.view(-1), self.returns.view(-1)
+        n_mb = self.pool_local // self.mb_local
+        losses = None
+        for _ in range(self.epochs):
+            perm = torch.randperm(self.pool_local, generator=self.gen, device=S.device, dtype=torch.int32)
+            for j in range(n_mb):
+                idx = perm[j * self.mb_local:(j + 1) * self.mb_local]
+                check(L.wb_gather_minibatch_dev(h, self.mb_local, ptr(idx), ptr(S), ptr(A), ptr(LP), ptr(ADV), ptr(RET), *[ptr(m) for m in self.mb]))
+                check(L.wb_ppo_grad_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
+                _dist.allreduce_sum_(self.grad_view)
+                check(L.wb_adam_step(h))
+        losses = self.grad_view[-3:].clone()  # [sum g_V, sum mean_k g_mu, skipped] of the last mini-batch (PPOAgent.cs:331-332)
+        return n_mb * self.epochs, losses
+
+    def iterate(self):
+        """One rollout + one update; returns a dict of device-timed statistics (this rank's share)."""
+        torch = self.torch
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        self.rollout()
+        e[1].record()
+        n_mb, losses = self.update()
+        e[2].record()
+        e[2].synchronize()
+        self.iterations += 1
+        return {"rollout_ms": e[0].elapsed_time(e[1]), "update_ms": e[1].elapsed_time(e[2]), "minibatches": n_mb,
+                "env_steps": self.n * self.T, "samples_trained": n_mb * self.mb_local,
+                "mean_reward": float(self.rewards.mean().item()), "episodes_finished": int(self.dones.sum().item()),
+                "losses": [float(x) for x in losses.tolist()]}
+
+    def weights_checksum(self) -> float:
+        """Sum of |w| over both networks -- identical on every rank when the data-parallel update is consistent."""
+        return float(np.abs(self.agent.actor.get_flat()).sum() + np.abs(self.agent.critic.get_flat()).sum())
+
+
+__all__ = ["VectorPPO"]
