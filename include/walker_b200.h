@@ -140,8 +140,9 @@ int32_t wb_env_step_dev(wb_env_batch* env, const float* actions_dev, float delta
                         float* reward_dev, uint8_t* done_dev);
 /* number of kernel launches this handle has issued (bench.py "gpu_launches") */
 int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out);
-/* lanes per environment of the physics kernel: 1 (one thread per walker: throughput, large batches), 2, 4, 8 or 16 (the lanes of
- * a walker split its SAT axes and vertices: latency, small batches); 0 = chosen from the batch size (the default) */
+/* physics kernel variant: 2, 4, 8 or 16 lanes per walker (the lanes split the two legs, the SAT axes and the vertices: latency,
+ * small batches), 1 (one thread per walker) or 1001 (one thread per walker + CTA-level work compaction: throughput, GPU full);
+ * 104/108/116 = lanes without the leg split (kept for comparison); 0 = chosen from the batch size (the default) */
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env);
 int32_t wb_env_get_variant(const wb_env_batch* env, int32_t* lanes_per_env_out);
 

@@ -156,7 +156,7 @@ static int default_lanes(int n_envs, int sm_count) {
   if (per_sm <= 64) return 8;
   if (per_sm <= 160) return 4;
   if (per_sm <= 320) return 2;
-  return 1;
+  return 1001;  // GPU full: one thread per walker with CTA-level work compaction
 }
 
 struct wb_env_batch {
@@ -165,7 +165,7 @@ struct wb_env_batch {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   wb_hyperparams hp{};
-  int lanes = 0;  // lanes per environment (1, 2, 4, 8, 16); 0 = chosen from the batch size at creation
+  int lanes = 0;  // kernel variant: lanes per environment (1, 2, 4, 8, 16) or 1001 (compacting); chosen from the batch size at creation
   int64_t launches = 0;
   // device state (structure of arrays)
   float* d_state = nullptr;    // [92][n_pad]
@@ -374,7 +374,7 @@ int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out) {
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env) {
   WB_REQUIRE(env, "env is null");
   if (lanes_per_env == 0) lanes_per_env = default_lanes(env->n, env->sm_count);
-  if (!physics_lanes_supported(lanes_per_env)) return fail(WB_ERR_INVALID, "lanes_per_env must be 1, 2, 4, 8 or 16 (or 104 / 108 / 116: no leg split)");
+  if (!physics_lanes_supported(lanes_per_env)) return fail(WB_ERR_INVALID, "variant must be 1, 2, 4, 8 or 16 lanes per walker, 104 / 108 / 116 (no leg split) or 1001 (compacting throughput kernel)");
   env->lanes = lanes_per_env;
   return WB_OK;
 }

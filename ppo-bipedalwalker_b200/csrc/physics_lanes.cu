@@ -58,9 +58,10 @@ constexpr int kFCount = 10;
 // edge P0 - P4, and edge 5 (P0 - P5) is the zero vector, which SATCollision.AxisChecks itself skips (SATCollision.cs:45).
 __device__ __forceinline__ int nverts(int b) { return b == BODY ? 5 : 6; }
 
-template <int L>
+template <int L_, int E_>
 struct Env {
-  static constexpr int E = 32 / L;  // environments per warp (= per CTA)
+  static constexpr int L = L_;  // lanes per environment
+  static constexpr int E = E_;  // environments (columns) per CTA
   float2* v2;   // this env's column of float2 slots: slot s at v2[s * E]
   float* f;     // this env's column of float slots
   const FloorConst* fl;  // the floor's constants (shared-memory copy: lanes index it with different runtime indices)
@@ -75,13 +76,13 @@ struct Env {
   float e_ww, mu_ww, e_wf, mu_wf;
 };
 
-template <int L> __device__ __forceinline__ float2& V2(const Env<L>& e, int slot) { return e.v2[slot * Env<L>::E]; }
-template <int L> __device__ __forceinline__ float& F1(const Env<L>& e, int slot) { return e.f[slot * Env<L>::E]; }
-template <int L> __device__ __forceinline__ float inv_inertia(const Env<L>& e, int b) { return b == BODY ? 0.0003f : e.ii_pole; }  // Walker.cs:168
+template <class EV> __device__ __forceinline__ float2& V2(const EV& e, int slot) { return e.v2[slot * EV::E]; }
+template <class EV> __device__ __forceinline__ float& F1(const EV& e, int slot) { return e.f[slot * EV::E]; }
+template <class EV> __device__ __forceinline__ float inv_inertia(const EV& e, int b) { return b == BODY ? 0.0003f : e.ii_pole; }  // Walker.cs:168
 template <int L> __device__ __forceinline__ void lanes_sync() { if (L > 1) __syncwarp(); }
 // true when `pred` holds on any lane of my env's group (full-mask vote: control flow is warp-uniform)
-template <int L, int G> __device__ __forceinline__ bool group_any(const Env<L>& e, bool pred) {
-  if (L == 1) return pred;
+template <class EV, int G> __device__ __forceinline__ bool group_any(const EV& e, bool pred) {
+  if (EV::L == 1) return pred;
   const unsigned b = __ballot_sync(kFull, pred);
   return ((b >> e.gshift) & ((1u << G) - 1u)) != 0u;
 }
@@ -91,7 +92,7 @@ struct BodyDyn {
   float w, im, ii;
 };
 
-template <int L> __device__ __forceinline__ BodyDyn load_dyn(const Env<L>& e, int b) {
+template <class EV> __device__ __forceinline__ BodyDyn load_dyn(const EV& e, int b) {
   BodyDyn d;
   d.c = V2(e, kV2Cen + b);
   d.v = V2(e, kV2Vel + b);
@@ -100,7 +101,7 @@ template <int L> __device__ __forceinline__ BodyDyn load_dyn(const Env<L>& e, in
   d.ii = inv_inertia(e, b);
   return d;
 }
-template <int L> __device__ __forceinline__ BodyDyn floor_dyn(const Env<L>& e) {
+template <class EV> __device__ __forceinline__ BodyDyn floor_dyn(const EV& e) {
   BodyDyn d;
   d.c = e.fl->cen;
   d.v = mk2(0.0f, 0.0f);
@@ -109,7 +110,7 @@ template <int L> __device__ __forceinline__ BodyDyn floor_dyn(const Env<L>& e) {
   d.ii = 0.0f;
   return d;
 }
-template <int L> __device__ __forceinline__ void store_dyn(const Env<L>& e, int b, const BodyDyn& d) {
+template <class EV> __device__ __forceinline__ void store_dyn(const EV& e, int b, const BodyDyn& d) {
   V2(e, kV2Vel + b) = d.v;
   F1(e, kFOmega + b) = d.w;
 }
@@ -149,8 +150,8 @@ __device__ __forceinline__ void apply_impulses(BodyDyn& A, BodyDyn& B, float2 n,
 
 // Skeleton.Move (Skeleton.cs:76-85) of up to two bodies, split over the G lanes of the working group: items 0..5 = A's six
 // vertex slots (the Body's mirror slot moves with its vertex 0), 6 = A's centroid, 7..13 the same for B.  Predicated by `on`.
-template <int L, int G>
-__device__ __forceinline__ void move_bodies(const Env<L>& e, bool on, int A, float2 dA, bool moveB, int B, float2 dB) {
+template <class EV, int G>
+__device__ __forceinline__ void move_bodies(const EV& e, bool on, int A, float2 dA, bool moveB, int B, float2 dB) {
 #pragma unroll
   for (int it0 = 0; it0 < 14; it0 += G) {
     const int it = it0 + e.gsub;
@@ -165,8 +166,8 @@ __device__ __forceinline__ void move_bodies(const Env<L>& e, bool on, int A, flo
 }
 
 // ---------------------------------------------------------------- Joint.Step, Joint.cs:31-41
-template <int L, bool TRACE>
-__device__ __forceinline__ void joint_step(const Env<L>& e, int A, int ia, int B, int ib, wb_joint_trace* tr) {
+template <class EV, bool TRACE>
+__device__ __forceinline__ void joint_step(const EV& e, int A, int ia, int B, int ib, wb_joint_trace* tr) {
   const float2 pA = V2(e, A * 6 + ia);
   const float2 pB = V2(e, B * 6 + ib);
   float2 ab = vsub(pB, pA);
@@ -184,8 +185,8 @@ __device__ __forceinline__ void joint_step(const Env<L>& e, int A, int ia, int B
   const float2 dB = vhalf(vmul(vneg(ab), depth));
   BodyDyn X = load_dyn(e, B);  // Manifold(bodyA := joint._bodyB, bodyB := joint._bodyA), Joint.cs:40
   BodyDyn Y = load_dyn(e, A);
-  lanes_sync<L>();  // every lane has read the pre-move points, centroids and velocities
-  move_bodies<L, L>(e, active, A, dA, true, B, dB);
+  lanes_sync<EV::L>();  // every lane has read the pre-move points, centroids and velocities
+  move_bodies<EV, EV::L>(e, active, A, dA, true, B, dB);
   X.c = vadd(X.c, dB);  // the impulse sees the POST-move centroids and joint points
   Y.c = vadd(Y.c, dA);
   const float2 contact = vhalf(vadd(vadd(pA, dA), vadd(pB, dB)));  // Vector2.Divide(p0 + p1, 2), Impulses.cs:35
@@ -197,7 +198,7 @@ __device__ __forceinline__ void joint_step(const Env<L>& e, int A, int ia, int B
     store_dyn(e, B, X);
     store_dyn(e, A, Y);
   }
-  lanes_sync<L>();
+  lanes_sync<EV::L>();
 }
 
 // ---------------------------------------------------------------- SAT, SATCollision.cs:15-104
@@ -245,8 +246,8 @@ __device__ __forceinline__ int support_index6(const float2 (&P)[6], float2 nrm) 
   return k;
 }
 
-template <int L>
-__device__ __forceinline__ Face significant_face_body(const Env<L>& e, int b, const float2 (&P)[6], float2 nrm) {
+template <class EV>
+__device__ __forceinline__ Face significant_face_body(const EV& e, int b, const float2 (&P)[6], float2 nrm) {
   const int n = nverts(b);
   const int k = support_index6(P, nrm);
   const int kn = (k + 1 == n) ? 0 : k + 1;
@@ -254,8 +255,8 @@ __device__ __forceinline__ Face significant_face_body(const Env<L>& e, int b, co
   return face_from(V2(e, b * 6 + k), V2(e, b * 6 + kn), V2(e, b * 6 + kp), nrm);
 }
 
-template <int L>
-__device__ __forceinline__ Face significant_face_floor(const Env<L>& e, float2 nrm) {
+template <class EV>
+__device__ __forceinline__ Face significant_face_floor(const EV& e, float2 nrm) {
   float best = FLT_MAX;
   int k = 0;
 #pragma unroll
@@ -362,8 +363,9 @@ __device__ __forceinline__ bool aabb_hit(float2 amin, float2 amax, float2 bmin, 
 // FLOORB = false: a leg segment A against the other segment B of its own leg (both dynamic poles)
 // FLOORB = true : a walker body A against the static floor (scene constants)
 // `want`: this env takes part (candidate exists at this position of its list order).
-template <int L, int G, bool TRACE, bool FLOORB>
-__device__ __forceinline__ void resolve_pair(Env<L>& e, bool want, int A, int B, wb_pair_trace* tr) {
+// `sep_axis` (may be null): receives the index (0..11, A's edges then B's) of the first separating axis this lane found
+template <class EV, int G, bool TRACE, bool FLOORB>
+__device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_pair_trace* tr, int* sep_axis = nullptr) {
   const FloorConst& fl = *e.fl;
   float2 PA[6], PB[6];
 #pragma unroll
@@ -413,7 +415,8 @@ __device__ __forceinline__ void resolve_pair(Env<L>& e, bool want, int A, int B,
         normal = axis;
         idx = axis_idx;
       }
-      const bool separated = group_any<L, G>(e, use && !overlapping);  // (a vote: every lane takes part, no short-circuit)
+      if (sep_axis != nullptr && use && !overlapping && !sep) *sep_axis = axis_idx;
+      const bool separated = group_any<EV, G>(e, use && !overlapping);  // (a vote: every lane takes part, no short-circuit)
       sep = sep || separated;
       return !__any_sync(kFull, hit && !sep);
     };
@@ -509,8 +512,8 @@ __device__ __forceinline__ void resolve_pair(Env<L>& e, bool want, int A, int B,
       // both dynamic -> A.Move(normal * depth / 2), B.Move(-normal * depth / 2)
       const float2 dA = FLOORB ? vmul(normal, depth) : vhalf(vmul(normal, depth));
       const float2 dB = FLOORB ? mk2(0.f, 0.f) : vhalf(vmul(vneg(normal), depth));
-      lanes_sync<L>();  // every lane has read the pre-move vertices, centroids and velocities
-      move_bodies<L, G>(e, colliding, A, dA, !FLOORB, B, dB);
+      lanes_sync<EV::L>();  // every lane has read the pre-move vertices, centroids and velocities
+      move_bodies<EV, G>(e, colliding, A, dA, !FLOORB, B, dB);
       if (ncp > 0) {  // impulses read the PRE-move velocities but the POST-move centroids
         X.c = vadd(X.c, dA);
         if (!FLOORB) Y.c = vadd(Y.c, dB);
@@ -520,7 +523,7 @@ __device__ __forceinline__ void resolve_pair(Env<L>& e, bool want, int A, int B,
           if (!FLOORB) store_dyn(e, B, Y);  // the floor is never written (inverse mass/inertia 0)
         }
       }
-      lanes_sync<L>();
+      lanes_sync<EV::L>();
     }
   }
   if (TRACE) {
@@ -530,8 +533,8 @@ __device__ __forceinline__ void resolve_pair(Env<L>& e, bool want, int A, int B,
 
 // ---------------------------------------------------------------- RigidBody.Step, RigidBody.cs:54-61,116-140
 // `on`: this lane group really steps body b (false for the right-leg half while the left-leg half steps the Body)
-template <int L, int G, bool TRACE>
-__device__ __forceinline__ void body_step(Env<L>& e, bool on, int b, float dt, wb_pair_trace* tr_base) {
+template <class EV, int G, bool TRACE>
+__device__ __forceinline__ void body_step(EV& e, bool on, int b, float dt, wb_pair_trace* tr_base) {
   // StepLinearVelocity: v += a * dt (gravity (0, 980), Walker.cs:45); Skeleton.Move(v * dt)
   float2 v = V2(e, kV2Vel + b);
   v = vadd(v, vmul(mk2(0.0f, 980.0f), dt));
@@ -547,7 +550,7 @@ __device__ __forceinline__ void body_step(Env<L>& e, bool on, int b, float dt, w
   rotz(theta, m11, m12);
   const float m21 = -m12, m22 = m11;
   const float2 cen = vadd(V2(e, kV2Cen + b), d);
-  lanes_sync<L>();  // all reads of the old centroid / velocity / angle are done
+  lanes_sync<EV::L>();  // all reads of the old centroid / velocity / angle are done
 #pragma unroll
   for (int i0 = 0; i0 < 6; i0 += G) {
     const int i = i0 + e.gsub;
@@ -566,7 +569,7 @@ __device__ __forceinline__ void body_step(Env<L>& e, bool on, int b, float dt, w
     V2(e, kV2Vel + b) = v;
     F1(e, kFAngle + b) = ang;
   }
-  lanes_sync<L>();
+  lanes_sync<EV::L>();
   // ResolveCollisions: candidates in Environment._rigidBodies order, skipping self and associated bodies (Walker.cs:204-208):
   // a leg segment meets the other segment of its own leg and the floor; the Body only the floor.  The floor comes first in the
   // list after the first Reset (Walker.cs:212-223).  Three uniform phases keep a warp whose environments disagree on the list
@@ -579,18 +582,18 @@ __device__ __forceinline__ void body_step(Env<L>& e, bool on, int b, float dt, w
     if (phase == 1) {
       const bool want = on && b != BODY;
       if (__any_sync(kFull, want))
-        resolve_pair<L, G, TRACE, false>(e, want, b, b == BODY ? LLL : partner, (TRACE && tr_base) ? tr_base + slot + (floor_first ? 1 : 0) : nullptr);
+        resolve_pair<EV, G, TRACE, false>(e, want, b, b == BODY ? LLL : partner, (TRACE && tr_base) ? tr_base + slot + (floor_first ? 1 : 0) : nullptr);
     } else {
       const bool want = on && ((b == BODY) ? (phase == 0) : ((phase == 0) == floor_first));
       if (__any_sync(kFull, want))
-        resolve_pair<L, G, TRACE, true>(e, want, b, FLOOR, (TRACE && tr_base) ? tr_base + slot + ((b == BODY || floor_first) ? 0 : 1) : nullptr);
+        resolve_pair<EV, G, TRACE, true>(e, want, b, FLOOR, (TRACE && tr_base) ? tr_base + slot + ((b == BODY || floor_first) ? 0 : 1) : nullptr);
     }
   }
 }
 
 // Walker.GetState, Walker.cs:132-152
-template <int L>
-__device__ __forceinline__ void store_observation(const Env<L>& e, float* dst) {  // dst is 16-byte aligned (48 B per env)
+template <class EV>
+__device__ __forceinline__ void store_observation(const EV& e, float* dst) {  // dst is 16-byte aligned (48 B per env)
   const float2 j0 = V2(e, BODY * 6 + 1), j2 = V2(e, LLU * 6 + 2), j3 = V2(e, RLU * 6 + 2), bv = V2(e, kV2Vel + BODY);
   float4* d4 = reinterpret_cast<float4*>(dst);
   d4[0] = make_float4(fdiv(j0.x, 900.0f), fdiv(j0.y, 500.0f), fdiv(j2.x, 900.0f), fdiv(j2.y, 500.0f));
@@ -600,9 +603,8 @@ __device__ __forceinline__ void store_observation(const Env<L>& e, float* dst) {
 
 // canonical record index f < 88 (walker_b200.h) -> word index inside a column set of E environments (env column 0);
 // rows 88..91 (joint torques) stay in HBM.  The float2 slots come first, then the float slots.
-template <int L>
+template <int E>
 __device__ __forceinline__ int record_word(int f) {
-  constexpr int E = 32 / L;
   if (f < 58) {
     const int vtx = f >> 1, slot = vtx + (vtx >= 17 ? 1 : 0);
     return slot * E * 2 + (f & 1);
@@ -627,11 +629,12 @@ __global__ void __launch_bounds__(32, 16) physics_lanes_kernel(const PhysicsPara
     const int f = idx / E, c = idx % E;
     const int env = env0 + c;
     const float v = (env < p.n) ? p.state[(size_t)f * p.n_pad + env] : c_init_state[f];
-    s_state[record_word<L>(f) + (f < 78 ? 2 * c : c)] = v;
+    s_state[record_word<E>(f) + (f < 78 ? 2 * c : c)] = v;
   }
   __syncwarp();
 
-  Env<L> e;
+  using EV = Env<L, E>;
+  EV e;
   const int col = lane / L;
   const int env = env0 + col;
   e.v2 = reinterpret_cast<float2*>(s_state) + col;
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(32, 16) physics_lanes_kernel(const PhysicsPara
     __syncwarp();
     if (on && e.sub == 0) {
 #pragma unroll 1
-      for (int f = 0; f < 88; f++) s_state[record_word<L>(f) + (f < 78 ? 2 * col : col)] = c_init_state[f];
+      for (int f = 0; f < 88; f++) s_state[record_word<E>(f) + (f < 78 ? 2 * col : col)] = c_init_state[f];
       V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
       for (int k = 0; k < 4; k++) torque_rows[(size_t)k * p.n_pad] = c_init_state[88 + k];
     }
@@ -717,12 +720,12 @@ __global__ void __launch_bounds__(32, 16) physics_lanes_kernel(const PhysicsPara
 #pragma unroll 1
       for (int k = 0; k < 4; k++) {
         const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
-        joint_step<L, TRACE>(e, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, jt ? jt + k : nullptr);
+        joint_step<EV, TRACE>(e, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, jt ? jt + k : nullptr);
       }
       // bodies in list order; the static floor's Update is a no-op (a = v = 0, returns before rotation/collisions)
       if (LEGS == 1) {
 #pragma unroll 1
-        for (int b = 0; b < 5; b++) body_step<L, L, TRACE>(e, e.live, b, dt, pt);
+        for (int b = 0; b < 5; b++) body_step<EV, L, TRACE>(e, e.live, b, dt, pt);
       } else {
         // {LLL, LLU, Body} on the first half of the env's lanes, {RLL, RLU} on the second: the three subsystems share no
         // mutable state during the sweep, so any interleaving reproduces the sequential list-order result bit for bit
@@ -733,7 +736,7 @@ __global__ void __launch_bounds__(32, 16) physics_lanes_kernel(const PhysicsPara
 #pragma unroll 1
         for (int k = 0; k < 3; k++) {
           const bool on = e.live && (leg == 0 || k < 2);
-          body_step<L, G, TRACE>(e, on, leg == 0 ? k : (k < 2 ? RLL + k : RLU), dt, pt);
+          body_step<EV, G, TRACE>(e, on, leg == 0 ? k : (k < 2 ? RLL + k : RLU), dt, pt);
         }
         e.gsub = e.sub;
         e.gshift = col * L;
@@ -788,7 +791,7 @@ __global__ void __launch_bounds__(32, 16) physics_lanes_kernel(const PhysicsPara
   // ---- write the records back (same coalesced pattern)
   for (int idx = lane; idx < 88 * E; idx += 32) {
     const int f = idx / E, c = idx % E;
-    if (env0 + c < p.n) p.state[(size_t)f * p.n_pad + env0 + c] = s_state[record_word<L>(f) + (f < 78 ? 2 * c : c)];
+    if (env0 + c < p.n) p.state[(size_t)f * p.n_pad + env0 + c] = s_state[record_word<E>(f) + (f < 78 ? 2 * c : c)];
   }
 }
 
@@ -843,6 +846,377 @@ static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t str
 
 }  // namespace pl
 
+// ================================================================ throughput kernel with CTA-level work compaction
+// One thread per environment (as L = 1 above), but a warp of the plain kernel executes the UNION of its 32 walkers' branches,
+// and in a decorrelated rollout the expensive branches are rare per walker yet almost always present in some lane: a leg
+// pair's AABBs overlap 85 % of the time but SAT finds a collision in only ~10 % of the substeps, the floor is touched in ~5 %,
+// a joint needs correcting in ~20 % (profiles/physics_r1_hotspots.md: 31 % of the executed lane-slots did useful work).
+// Here the CTA (128 walkers) advances in lockstep PHASES, and each phase has two stages:
+//   stage 1  every thread, for ITS walker: the cheap, common part -- integrate the body; for a leg pair test the separating
+//            axis that separated this pair last time (temporal coherence; any order of the axis tests gives the reference's
+//            result: if one axis separates, SATCollision.IsColliding is false whatever the others say), then the AABBs; for
+//            a floor pair the AABBs (and the Collided latch); for a joint the gap.  Walkers that need the expensive part
+//            push an item (walker, body / joint) onto a queue in shared memory.
+//   stage 2  after a CTA barrier, the queued items are processed DENSELY: thread t takes item t (any thread can work on any
+//            walker: the state columns live in shared memory), runs the full resolve_pair / joint_step of the plain kernel
+//            on that walker's columns and records the separating axis it found, if any, for the next substep.
+// Left and right leg are swept in the same phase (they share no mutable state, see the leg split above), which halves the
+// number of barriers and doubles the queue density.  Arithmetic and order per walker are those of the plain kernel: the
+// results are bit-identical (tests/test_physics_gpu.py runs every variant against the oracle).
+namespace pc {
+using namespace pl;
+
+constexpr int kE = 128;  // walkers (= threads) per CTA
+using EV = Env<1, kE>;
+
+struct Shared {
+  float state[(kV2Count * 2 + kFCount) * kE];
+  float mat[6 * kE];            // im_w, ii_pole, e_ww, mu_ww, e_wf, mu_wf per walker (stage 2 works on other walkers)
+  FloorConst floor;
+  unsigned char axis[4 * kE];   // last separating axis per ordered leg pair {LLL->LLU, LLU->LLL, RLL->RLU, RLU->RLL}
+  unsigned short queue[2 * kE];
+  int count[2];  // ping-pong: the counter of the next round is cleared while the current one drains
+};
+
+__device__ __forceinline__ void env_for_column(EV& e, Shared& S, int col, bool live) {
+  e.v2 = reinterpret_cast<float2*>(S.state) + col;
+  e.f = S.state + kV2Count * kE * 2 + col;
+  e.fl = &S.floor;
+  e.sub = 0;
+  e.gsub = 0;
+  e.gshift = 0;
+  e.live = live;
+  e.flags = 0;
+  e.im_w = S.mat[0 * kE + col];
+  e.ii_pole = S.mat[1 * kE + col];
+  e.e_ww = S.mat[2 * kE + col];
+  e.mu_ww = S.mat[3 * kE + col];
+  e.e_wf = S.mat[4 * kE + col];
+  e.mu_wf = S.mat[5 * kE + col];
+}
+
+// queue push: one shared-memory atomic per warp
+__device__ __forceinline__ void push(Shared& S, int parity, bool want, int item) {
+  const unsigned m = __ballot_sync(kFull, want);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&S.count[parity], __popc(m));
+  base = __shfl_sync(kFull, base, 0);
+  if (want) S.queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)item;
+}
+
+// stage 1 of a leg pair: true when the pair needs the full narrow phase.  Tests the cached axis first (a separating axis
+// settles the pair: no collision, nothing else to do), then the bounding boxes.
+__device__ __noinline__ bool pole_pair_needs_work(const EV& e, int A, int B, int cached) {
+  float2 PA[6], PB[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) PA[i] = V2(e, A * 6 + i);
+#pragma unroll
+  for (int i = 0; i < 6; i++) PB[i] = V2(e, B * 6 + i);
+  const int own = cached < 6 ? A : B;
+  const int k = cached < 6 ? cached : cached - 6;
+  const float2 p0 = V2(e, own * 6 + k), p1 = V2(e, own * 6 + (k == 5 ? 0 : k + 1));
+  const float2 edge = vsub(p1, p0);
+  float2 axis = mk2(-edge.y, edge.x);
+  const bool skip = (axis.x == 0.0f) && (axis.y == 0.0f);
+  axis = vnormalize_fast(axis);
+  float amn, amx, bmn, bmx;
+  project6(PA, axis, amn, amx);
+  project6(PB, axis, bmn, bmx);
+  const bool overlapping = (amn < bmx) && (bmn < amx);
+  if (!skip && !overlapping) return false;  // AxisChecks would return false at this axis
+  float2 amin, amax, bmin, bmax;
+  aabb6(PA, amin, amax);
+  aabb6(PB, bmin, bmax);
+  return aabb_hit(amin, amax, bmin, bmax);
+}
+
+// stage 1 of a floor pair: bounding boxes + the Collided latch (RigidBody.cs:73-76)
+__device__ __noinline__ bool floor_pair_needs_work(EV& e, int A) {
+  float2 PA[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) PA[i] = V2(e, A * 6 + i);
+  float2 amin, amax;
+  aabb6(PA, amin, amax);
+  const bool hit = aabb_hit(amin, amax, e.fl->bb_min, e.fl->bb_max);
+  if (hit) e.flags |= (1 << A);
+  return hit;
+}
+
+// RigidBody.StepLinearVelocity / StepAngularVelocity / Skeleton.Move / Rotate of one body (the first half of body_step)
+__device__ __noinline__ void integrate_body(const EV& e, int b, float dt) {
+  float2 v = V2(e, kV2Vel + b);
+  v = vadd(v, vmul(mk2(0.0f, 980.0f), dt));
+  const float2 d = vmul(v, dt);
+  const float w = F1(e, kFOmega + b);
+  const float theta = fmul(w, dt);
+  float ang = fadd(F1(e, kFAngle + b), theta);
+  const float PI_F = 3.14159274f, TAU_F = 6.28318548f;
+  if (ang > PI_F) ang = fsub(ang, TAU_F);
+  else if (ang < -PI_F) ang = fadd(ang, TAU_F);
+  float m11, m12;
+  rotz(theta, m11, m12);
+  const float m21 = -m12, m22 = m11;
+  const float2 cen = vadd(V2(e, kV2Cen + b), d);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float2 p = vadd(V2(e, b * 6 + i), d);
+    p = vsub(p, cen);
+    float2 t;
+    t.x = fadd(fadd(fmul(p.x, m11), fmul(p.y, m21)), 0.0f);
+    t.y = fadd(fadd(fmul(p.x, m12), fmul(p.y, m22)), 0.0f);
+    V2(e, b * 6 + i) = vadd(t, cen);
+  }
+  V2(e, kV2Cen + b) = cen;
+  V2(e, kV2Vel + b) = v;
+  F1(e, kFAngle + b) = ang;
+}
+
+__device__ __forceinline__ int pair_slot(int b) { return b == LLL ? 0 : b == LLU ? 1 : b == RLL ? 2 : 3; }
+__device__ __forceinline__ int partner_of(int b) { return (0x34F01 >> (4 * b)) & 0xF; }  // {LLU, LLL, -, RLU, RLL}
+
+enum { kItemPole = 0, kItemFloor = 1, kItemJoint = 2 };
+
+// stage 2: the queued items, densely, kG lanes per item (the lanes split the SAT axes and the vertices of the moves exactly
+// like the L > 1 layouts of the plain kernel; with ~15-20 % of the walkers queued per round this keeps most warps of the CTA
+// busy and roughly halves the latency of the round).  Item = walker column | payload << 7.
+constexpr int kG = 2;
+using EVG = Env<kG, kE>;
+
+__device__ __forceinline__ void group_env_for_column(EVG& e, Shared& S, int col, bool live) {
+  e.v2 = reinterpret_cast<float2*>(S.state) + col;
+  e.f = S.state + kV2Count * kE * 2 + col;
+  e.fl = &S.floor;
+  e.sub = threadIdx.x % kG;
+  e.gsub = e.sub;
+  e.gshift = ((threadIdx.x & 31) / kG) * kG;
+  e.live = live;
+  e.flags = 0;
+  e.im_w = S.mat[0 * kE + col];
+  e.ii_pole = S.mat[1 * kE + col];
+  e.e_ww = S.mat[2 * kE + col];
+  e.mu_ww = S.mat[3 * kE + col];
+  e.e_wf = S.mat[4 * kE + col];
+  e.mu_wf = S.mat[5 * kE + col];
+}
+
+template <int KIND>
+__device__ __noinline__ void drain(Shared& S, int parity) {
+  const int count = S.count[parity];
+  const int warp_base = (threadIdx.x >> 5) * (32 / kG), lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int base = warp_base; base < count; base += kE / kG) {
+    const int slot = base + lane / kG;
+    const bool valid = slot < count;
+    const int item = valid ? S.queue[slot] : 0;
+    const int col = item & 127, payload = item >> 7;
+    EVG q;
+    group_env_for_column(q, S, col, valid);
+    if (KIND == kItemPole) {
+      int sep_axis = -1;
+      resolve_pair<EVG, kG, false, false>(q, valid, payload, partner_of(payload), nullptr, &sep_axis);
+      // the lane that saw the lowest separating axis of the group records it (any separating axis is a valid cache entry)
+      if (valid && sep_axis >= 0) S.axis[pair_slot(payload) * kE + col] = (unsigned char)sep_axis;
+    } else if (KIND == kItemFloor) {
+      resolve_pair<EVG, kG, false, true>(q, valid, payload, FLOOR, nullptr);
+    } else {
+      const int k = payload;
+      const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
+      joint_step<EVG, false>(q, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, nullptr);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kE, 4) physics_compact_kernel(const PhysicsParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Shared& S = *reinterpret_cast<Shared*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int env0 = blockIdx.x * kE;
+  const int env = env0 + tid;
+  const bool live = env < p.n;
+  const int envc = live ? env : 0;
+
+  for (int w = tid; w < (int)(sizeof(FloorConst) / 4); w += kE)
+    reinterpret_cast<uint32_t*>(&S.floor)[w] = reinterpret_cast<const uint32_t*>(&c_floor)[w];
+  // stage the record of my walker (SoA rows are contiguous over walkers: coalesced)
+#pragma unroll 8
+  for (int f = 0; f < 88; f++)
+    S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = live ? p.state[(size_t)f * p.n_pad + env] : c_init_state[f];
+  {
+    const Material mw = c_materials[p.walker_mat[envc]];
+    const Material mf = c_materials[p.floor_mat[envc]];
+    S.mat[0 * kE + tid] = mw.inverse_mass;
+    S.mat[1 * kE + tid] = fmul(0.001f, mw.inverse_mass);
+    S.mat[2 * kE + tid] = net_max(mw.restitution, mw.restitution);
+    S.mat[3 * kE + tid] = net_min(mw.friction, mw.friction);
+    S.mat[4 * kE + tid] = net_max(mw.restitution, mf.restitution);
+    S.mat[5 * kE + tid] = net_min(mw.friction, mf.friction);
+  }
+#pragma unroll
+  for (int s = 0; s < 4; s++) S.axis[s * kE + tid] = 0;
+  if (tid == 0) S.count[0] = S.count[1] = 0;
+  EV e;
+  env_for_column(e, S, tid, live);
+  V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
+  float* torque_rows = p.state + (size_t)88 * p.n_pad + envc;
+  e.flags = p.flags[envc];
+  int steps = p.steps[envc];
+  float2 pos = mk2(p.pos[envc], p.pos[p.n_pad + envc]);
+
+  auto write_initial_record = [&]() {  // Walker.Reset + CreateCreature (own walker only: no synchronisation needed)
+#pragma unroll 1
+    for (int f = 0; f < 88; f++) S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = c_init_state[f];
+    V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
+    for (int k = 0; k < 4; k++) torque_rows[(size_t)k * p.n_pad] = c_init_state[88 + k];
+  };
+
+  if (p.phases & kPhaseResetMasked) {
+    if (live && (p.reset_mask == nullptr || p.reset_mask[envc])) {
+      write_initial_record();
+      e.flags = (p.phases & kPhaseFirstEpisode) ? 0 : WB_FLAG_FLOOR_FIRST;
+      steps = 0;
+      pos = V2(e, kV2Cen + BODY);
+    }
+  }
+  if (p.phases & kPhaseIncSteps) steps++;
+  if ((p.phases & kPhaseTakeActions) && live) {
+    const float4 a4 = *reinterpret_cast<const float4*>(p.actions + (size_t)env * 4);
+    const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float a = act[k];
+      if (a >= 1.0f) a = 1.0f;
+      else if (a <= -1.0f) a = -1.0f;
+      const float change = fsub(a, torque_rows[(size_t)k * p.n_pad]);
+      torque_rows[(size_t)k * p.n_pad] = a;
+      const int bodyB = (k == 0) ? LLU : (k == 1) ? RLU : (k == 2) ? LLL : RLL;
+      F1(e, kFOmega + bodyB) = fadd(F1(e, kFOmega + bodyB), fmul(change, 5.0f));
+    }
+  }
+
+  if (p.phases & kPhaseStepObjects) {
+    const float dt = fdiv(p.dt, (float)p.iterations);
+    const bool floor_first = (e.flags & WB_FLAG_FLOOR_FIRST) != 0;
+    // which floor sub-phases this CTA needs at all (the list order only changes at a reset, never inside the sweep)
+    // padding threads (env >= n) sweep a scratch copy of the initial walker like everybody else -- no thread of the CTA ever
+    // leaves the lockstep -- and simply never store anything to global memory
+    const bool any_first = __syncthreads_or(floor_first) != 0;
+    const bool any_last = __syncthreads_or(!floor_first) != 0;
+
+    auto joint_gap_active = [&](int k) {
+      const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
+      const float2 ab = vsub(V2(e, B * 6 + (k < 2 ? 4 : 3)), V2(e, A * 6 + (k < 2 ? 1 : 2)));
+      const float depth = fsqrt(fadd(fmul(ab.x, ab.x), fmul(ab.y, ab.y)));
+      return !(depth < 0.1f);
+    };
+    // one queue round: (stage 1 already pushed) barrier, drain, barrier; the other counter is cleared in between
+    int parity = 0;
+    auto round = [&](auto drain_fn) {
+      __syncthreads();
+      if (tid == 0) S.count[parity ^ 1] = 0;
+      drain_fn();
+      __syncthreads();
+      parity ^= 1;
+    };
+
+#pragma unroll 1
+    for (int it = 0; it < p.iterations; it++) {
+      // ---- joints in creation order; (Body,RLU) and (LLU,LLL) touch disjoint bodies and share a round
+      push(S, parity, joint_gap_active(0), tid | (0 << 7));
+      round([&] { drain<kItemJoint>(S, parity); });
+      push(S, parity, joint_gap_active(1), tid | (1 << 7));
+      push(S, parity, joint_gap_active(2), tid | (2 << 7));
+      round([&] { drain<kItemJoint>(S, parity); });
+      push(S, parity, joint_gap_active(3), tid | (3 << 7));
+      round([&] { drain<kItemJoint>(S, parity); });
+      // ---- body sweep: {LLL, RLL}, {LLU, RLU}, {Body}; per body [floor if floor-first] [leg partner] [floor if floor-last]
+#pragma unroll 1
+      for (int ph = 0; ph < 3; ph++) {
+        const int b0 = ph == 0 ? LLL : ph == 1 ? LLU : BODY;
+        const int b1 = ph == 0 ? RLL : RLU;
+        const int nb = ph == 2 ? 1 : 2;
+        integrate_body(e, b0, dt);
+        if (nb == 2) integrate_body(e, b1, dt);
+        if (ph == 2) {
+          push(S, parity, floor_pair_needs_work(e, BODY), tid | (BODY << 7));
+          round([&] { drain<kItemFloor>(S, parity); });
+          continue;
+        }
+        if (any_first) {
+          push(S, parity, floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 7));
+          push(S, parity, floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 7));
+          round([&] { drain<kItemFloor>(S, parity); });
+        }
+        push(S, parity, pole_pair_needs_work(e, b0, partner_of(b0), S.axis[pair_slot(b0) * kE + tid]), tid | (b0 << 7));
+        push(S, parity, pole_pair_needs_work(e, b1, partner_of(b1), S.axis[pair_slot(b1) * kE + tid]), tid | (b1 << 7));
+        round([&] { drain<kItemPole>(S, parity); });
+        if (any_last) {
+          push(S, parity, !floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 7));
+          push(S, parity, !floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 7));
+          round([&] { drain<kItemFloor>(S, parity); });
+        }
+      }
+    }
+  }
+
+  if (p.phases & kPhaseObserve) {
+    const float2 prev = pos;
+    pos = V2(e, kV2Cen + BODY);
+    if (e.flags & ((1 << BODY) | (1 << LLU) | (1 << RLU))) e.flags |= WB_FLAG_TERMINAL;
+    const float dx = fsub(pos.x, prev.x);
+    const float h = fdiv(V2(e, BODY * 6 + 1).y, 500.0f);
+    float r = 0.0f;
+    r = fadd(r, (dx > 0.0f && h < 1.6f) ? dx : 0.0f);
+    r = fsub(r, (h > 1.65f) ? -0.1f : 0.0f);
+    bool terminal = false;
+    if ((e.flags & WB_FLAG_TERMINAL) || steps > p.max_timesteps) {
+      if (e.flags & WB_FLAG_TERMINAL) r = fsub(r, 40.0f);
+      terminal = true;
+    }
+    if (pos.x > 900.0f) {
+      r = fadd(r, 80.0f);
+      terminal = true;
+    }
+    if (live && terminal && (p.phases & kPhaseAutoReset)) {
+      write_initial_record();
+      e.flags = WB_FLAG_FLOOR_FIRST;
+      steps = 0;
+      pos = V2(e, kV2Cen + BODY);
+    }
+    if (live) {
+      store_observation(e, p.obs + (size_t)env * WB_OBS);
+      p.reward[env] = r;
+      p.done[env] = terminal ? 1 : 0;
+    }
+  } else if (p.phases & kPhaseObsOnly) {
+    if (live) store_observation(e, p.obs + (size_t)env * WB_OBS);
+  }
+
+  if (live) {
+    p.flags[env] = e.flags;
+    p.steps[env] = steps;
+    p.pos[env] = pos.x;
+    p.pos[p.n_pad + env] = pos.y;
+#pragma unroll 8
+    for (int f = 0; f < 88; f++) p.state[(size_t)f * p.n_pad + env] = S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)];
+  }
+}
+
+static cudaError_t launch_compact(const PhysicsParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(physics_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  physics_compact_kernel<<<(p.n + kE - 1) / kE, kE, sizeof(Shared), stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pc
+
+
 // ---------------------------------------------------------------- host side
 cudaError_t upload_materials(const Material* table, int count) {
   return cudaMemcpyToSymbol(pl::c_materials, table, sizeof(Material) * count);
@@ -854,11 +1228,12 @@ cudaError_t upload_scene_constants(const float* init_state92, const FloorConst* 
   return cudaMemcpyToSymbol(pl::c_floor, floor, sizeof(FloorConst));
 }
 
-// variant code = lanes per environment (1, 2, 4, 8, 16; for >= 2 the lanes split by leg first), or 100 + lanes (4, 8, 16) for
-// the measured-for-comparison layout without the leg split (all lanes of a walker work on one pair)
+// variant code = lanes per environment (1, 2, 4, 8, 16; for >= 2 the lanes split by leg first), 100 + lanes (4, 8, 16) for
+// the measured-for-comparison layout without the leg split (all lanes of a walker work on one pair), or 1001 = one thread
+// per walker with CTA-level work compaction (the throughput kernel)
 bool physics_lanes_supported(int variant) {
   switch (variant) {
-    case 1: case 2: case 4: case 8: case 16: case 104: case 108: case 116: return true;
+    case 1: case 2: case 4: case 8: case 16: case 104: case 108: case 116: case 1001: return true;
     default: return false;
   }
 }
@@ -873,6 +1248,7 @@ cudaError_t launch_physics(const PhysicsParams& p, int variant, bool trace, cuda
     case 104: return pl::launch_l<4, 1>(p, trace, stream);
     case 108: return pl::launch_l<8, 1>(p, trace, stream);
     case 116: return pl::launch_l<16, 1>(p, trace, stream);
+    case 1001: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact(p, stream);  // (the trace hook uses the plain kernel)
     default: return cudaErrorInvalidValue;
   }
 }
