@@ -163,7 +163,21 @@ cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M,
 // ============================================================================================================
 constexpr int kS = 64;           // samples per tile
 constexpr int kBlk = kS * 32;    // floats in one 32-feature block of a 64-row tile (8 KB)
-constexpr int kTcThreads = 160;   // warps 0..3: one TMEM sub-partition each (epilogue / per-sample math); warp 4: MMA issuer
+// warps 0..7: epilogue / per-sample math -- warp w works on TMEM sub-partition w % 4 (the 16 rows an M=64 accumulator keeps
+// there) and on HALF w / 4 of the columns of every phase (half 0: A1, G1 and columns 0..31 of A2/G2; half 1: C1, value, gv,
+// Gc1 and columns 32..63 of A2/G2), so the per-sample element-wise work of a tile is spread over 128 threads; warp 8: MMA issuer
+constexpr int kTcThreads = 288;
+
+// ---- pre-built MMA programs.  All operand tiles live at fixed shared-memory addresses, so every tcgen05.mma of a tile's
+// pipeline (150 of them) has constant descriptors: they are built ONCE per CTA, in parallel, into a table, and the issuing
+// thread only streams entries (one LDS.128 pair + one tcgen05.mma each) instead of rebuilding 64-bit descriptors per k-step.
+struct __align__(16) MmaEntry {
+  uint64_t da, db;
+  uint32_t tmem_col, idesc;
+  uint32_t acc_mode;  // 0: overwrite (first MMA of a fresh accumulator), 1: accumulate, 2: accumulate unless first tile of the CTA
+  uint32_t pad;
+};
+constexpr int kChainF1 = 0, kChainF2 = 6, kChainDW3 = 30, kChainB2 = 54, kChainDW2 = 78, kChainDB2 = 102, kChainDW1 = 126, kMmaEntries = 150;
 
 struct __align__(1024) TcSmem {
   float xt_hi[kBlk], xt_lo[kBlk];            // [X(12) | 1 | 0 0 0] per sample
@@ -172,7 +186,9 @@ struct __align__(1024) TcSmem {
   float w2_hi[2 * kBlk], w2_lo[2 * kBlk];    // rows = o (64), features = i (64)
   float w1_hi[128 * 32], w1_lo[128 * 32];    // rows = [W1 o | Wc1 o] (128), features = [i(12) | bias | 0 0 0]
   float w3[kAct * kHid], wc2[kHid], b2[kHid], b3[kAct], bc2[4];
-  float red[256];
+  float mu_part[2][kS][kAct];  // the two halves' partial W3 . A2 sums
+  MmaEntry mma[kMmaEntries];
+  float red[512];
   uint64_t mbar;
   uint32_t tmem_slot;
 };
@@ -205,6 +221,39 @@ __device__ __forceinline__ void issue_chain(uint32_t tmem_d, int M, int N, const
       tc::mma_tf32(tmem_d, da, db, idesc, acc);
       acc = true;
     }
+  }
+}
+
+// entries [first, first + 3 * ksteps) = one 3xTF32 chain (same operand addressing as issue_chain); `persistent`: the
+// accumulator lives across tiles (weight gradients)
+__device__ __forceinline__ void build_chain(MmaEntry* table, int first, uint32_t tmem_col, int M, int N, const float* a_hi, const float* a_lo,
+                                            int a_major, int a_rows, const float* b_hi, const float* b_lo, int b_major, int b_rows, int ksteps,
+                                            bool persistent) {
+  const uint32_t idesc = tc::make_idesc_tf32(M, N, a_major, b_major);
+  const uint32_t a_lbo = a_major == kMnMajor ? (uint32_t)a_rows * 128u : 0u;
+  const uint32_t b_lbo = b_major == kMnMajor ? (uint32_t)b_rows * 128u : 0u;
+  for (int i = threadIdx.x; i < 3 * ksteps; i += blockDim.x) {
+    const int pass = i / ksteps, ks = i % ksteps;
+    const uint32_t a_base = tc::smem_u32(pass == 1 ? a_lo : a_hi);
+    const uint32_t b_base = tc::smem_u32(pass == 2 ? b_lo : b_hi);
+    const uint32_t a_off = a_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * a_rows * 128u + (uint32_t)(ks & 3) * 32u;
+    const uint32_t b_off = b_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * b_rows * 128u + (uint32_t)(ks & 3) * 32u;
+    MmaEntry e;
+    e.da = tc::make_smem_desc(a_base + a_off, a_lbo, 512u) | kLayoutB32;
+    e.db = tc::make_smem_desc(b_base + b_off, b_lbo, 512u) | kLayoutB32;
+    e.tmem_col = tmem_col;
+    e.idesc = idesc;
+    e.acc_mode = i > 0 ? 1u : (persistent ? 2u : 0u);
+    e.pad = 0u;
+    table[first + i] = e;
+  }
+}
+
+__device__ __forceinline__ void issue_range(const MmaEntry* table, int begin, int end, uint32_t tmem, bool any_tile) {
+#pragma unroll 4
+  for (int i = begin; i < end; i++) {
+    const MmaEntry e = table[i];
+    tc::mma_tf32(tmem + e.tmem_col, e.da, e.db, e.idesc, e.acc_mode == 1u || (e.acc_mode == 2u && any_tile));
   }
 }
 
@@ -249,10 +298,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool epi = warp < 4;                       // epilogue warps own TMEM lanes 32w..32w+31
+  const bool epi = warp < 8;                       // epilogue warps: TMEM sub-partition warp % 4 (lanes 32(w%4)..+31)
+  const int half = (warp >> 2) & 1;                // which half of every column block this warp owns (see header comment)
   const bool is_sample = epi && lane < 16;         // lanes 32w..32w+15 hold rows 16w..16w+15 of an M=64 accumulator
   const int s_loc = (warp & 3) * 16 + (lane & 15);
-  const bool issuer = tid == 128;                  // lane 0 of the dedicated issuer warp: tcgen05.mma / commit
+  const bool issuer = tid == 256;                  // lane 0 of the dedicated issuer warp: tcgen05.mma / commit
   const bool grad = p.mode == kModeGrad;
 
   if (warp == 0) tc::tmem_alloc(&S.tmem_slot, kTmemCols);
@@ -301,6 +351,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   }
   if (tid < kAct) S.b3[tid] = p.params[kOffB3 + tid];
   if (tid == 0) S.bc2[0] = p.params[kOffBc2];
+  build_chain(S.mma, kChainF1, kColF1, 64, 128, S.xt_hi, S.xt_lo, kKMajor, kS, S.w1_hi, S.w1_lo, kKMajor, 128, 2, false);
+  build_chain(S.mma, kChainF2, kColF2, 64, 64, S.act_hi, S.act_lo, kKMajor, kS, S.w2_hi, S.w2_lo, kKMajor, kHid, 8, false);
+  build_chain(S.mma, kChainDW3, kColDW3, 128, 8, S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, kMnMajor, kS, S.g3v_hi, S.g3v_lo, kMnMajor, kS, 8, true);
+  build_chain(S.mma, kChainB2, kColB2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kKMajor, kS, S.w2_hi, S.w2_lo, kMnMajor, kHid, 8, false);
+  build_chain(S.mma, kChainDW2, kColDW2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.act_hi, S.act_lo, kMnMajor, kS, 8, true);
+  build_chain(S.mma, kChainDB2, kColDB2, 64, 16, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, true);
+  build_chain(S.mma, kChainDW1, kColDW1, 128, 16, S.act_hi, S.act_lo, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, true);
   tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -338,7 +395,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     // ---- P1: F1 = [X|1] x [W1|b1 ; Wc1|bc1]^T  -> 128 columns
     if (issuer) {
-      issue_chain(tmem + kColF1, 64, 128, S.xt_hi, S.xt_lo, kKMajor, kS, S.w1_hi, S.w1_lo, kKMajor, 128, 2, false);
+      issue_range(S.mma, kChainF1, kChainF2, tmem, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -346,32 +403,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncwarp();
     tc::fence_after_thread_sync();
 
-    // ---- P2: A1 = leaky(.), C1 = leaky(.), V = Wc2 . C1 + bc2 (left-to-right), derivative masks
-    unsigned long long maskA1 = 0, maskC1 = 0, maskA2 = 0;
+    // ---- P2: half 0: A1 = leaky(F1[:, 0:64]); half 1: C1 = leaky(F1[:, 64:128]), V = Wc2 . C1 + bc2 (left to right).
+    //      The sign masks (LeakyReLU derivative) stay with the half that owns the columns.
+    unsigned mask1[2] = {0u, 0u};  // half 0: A1 < 0 per column; half 1: C1 < 0 per column
     float value = 0.f;
-    if (epi)
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 16) {
-      float v[16];
-      tc::tmem_ld_x16(tmem_warp + kColF1 + c, v);
-      tc::tmem_ld_wait();
+    if (epi) {
+      float* hi_t = S.act_hi + half * 2 * kBlk;
+      float* lo_t = S.act_lo + half * 2 * kBlk;
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        v[j] = tc_leaky(v[j]);
-        const unsigned long long neg = v[j] < 0.0f ? 1ull : 0ull;
-        if (c < 64) {
-          maskA1 |= neg << (c + j);
-        } else {
-          maskC1 |= neg << (c - 64 + j);
-          value = fmaf(v[j], S.wc2[c - 64 + j], value);
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tc::tmem_ld_x32(tmem_warp + kColF1 + half * 64 + c, v);
+        tc::tmem_ld_wait();
+        unsigned m = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          v[j] = tc_leaky(v[j]);
+          m |= (v[j] < 0.0f ? 1u : 0u) << j;
+        }
+        mask1[c >> 5] = m;
+        if (half == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) value = fmaf(v[j], S.wc2[c + j], value);
+        }
+        if (is_sample) {
+#pragma unroll
+          for (int u = 0; u < 32; u += 8) store_unit(hi_t, lo_t, s_loc, c + u, v + u);
         }
       }
-      if (is_sample) {
-        store_unit(S.act_hi, S.act_lo, s_loc, c, v);
-        store_unit(S.act_hi, S.act_lo, s_loc, c + 8, v + 8);
-      }
+      value += S.bc2[0];
     }
-    value += S.bc2[0];
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     __syncthreads();
@@ -379,7 +440,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     // ---- P3: F2 = A1 x W2^T
     if (issuer) {
-      issue_chain(tmem + kColF2, 64, 64, S.act_hi, S.act_lo, kKMajor, kS, S.w2_hi, S.w2_lo, kKMajor, kHid, 8, false);
+      issue_range(S.mma, kChainF2, kChainDW3, tmem, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -387,32 +448,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncwarp();
     tc::fence_after_thread_sync();
 
-    // ---- P4: A2 = leaky(. + b2); mu = tanh(W3 . A2 + b3) accumulated left to right
-    float mu[kAct] = {0.f, 0.f, 0.f, 0.f};
-    if (epi)
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 16) {
-      float v[16];
-      tc::tmem_ld_x16(tmem_warp + kColF2 + c, v);
+    // ---- P4: each half: A2 = leaky(F2 + b2) for its 32 columns and its partial W3 . A2; the partials meet in shared memory
+    unsigned maskA2 = 0u;  // own 32 columns
+    if (epi) {
+      const int c0 = half * 32;
+      float v[32];
+      float part[kAct] = {0.f, 0.f, 0.f, 0.f};
+      tc::tmem_ld_x32(tmem_warp + kColF2 + c0, v);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        v[j] = tc_leaky(v[j] + S.b2[c + j]);
-        maskA2 |= (v[j] < 0.0f ? 1ull : 0ull) << (c + j);
+      for (int j = 0; j < 32; j++) {
+        v[j] = tc_leaky(v[j] + S.b2[c0 + j]);
+        maskA2 |= (v[j] < 0.0f ? 1u : 0u) << j;
 #pragma unroll
-        for (int k = 0; k < kAct; k++) mu[k] = fmaf(v[j], S.w3[k * kHid + c + j], mu[k]);
+        for (int k = 0; k < kAct; k++) part[k] = fmaf(v[j], S.w3[k * kHid + c0 + j], part[k]);
       }
-      if (is_sample && grad) {
-        store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c, v);
-        store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c + 8, v + 8);
+      if (is_sample) {
+        if (grad) {
+#pragma unroll
+          for (int u = 0; u < 32; u += 8) store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c0 + u, v + u);
+        }
+        *reinterpret_cast<float4*>(&S.mu_part[half][s_loc][0]) = make_float4(part[0], part[1], part[2], part[3]);
       }
     }
-#pragma unroll
-    for (int k = 0; k < kAct; k++) mu[k] = tanhf(mu[k] + S.b3[k]);
+    __syncthreads();
+    float mu[kAct] = {0.f, 0.f, 0.f, 0.f};
+    if (epi) {  // all 32 lanes: lanes 16..31 shadow the sample of lane - 16 (they take half of its action dimensions below)
+      const float4 a = *reinterpret_cast<const float4*>(&S.mu_part[0][s_loc][0]);
+      const float4 b = *reinterpret_cast<const float4*>(&S.mu_part[1][s_loc][0]);
+      mu[0] = tanhf((a.x + b.x) + S.b3[0]);
+      mu[1] = tanhf((a.y + b.y) + S.b3[1]);
+      mu[2] = tanhf((a.z + b.z) + S.b3[2]);
+      mu[3] = tanhf((a.w + b.w) + S.b3[3]);
+    }
 
     if (!grad) {
-      if (valid) {
-        if (p.value) p.value[gs] = value;
+      if (valid && half == 1 && p.value) p.value[gs] = value;
+      if (valid && half == 0) {
 #pragma unroll
         for (int k = 0; k < kAct; k++) {
           if (p.mean) p.mean[(size_t)gs * kAct + k] = mu[k];
@@ -439,47 +511,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       continue;
     }
 
-    // ---- per-sample clipped-surrogate gradient (PPOAgent.cs:232-326), tanh backward
+    // ---- per-sample clipped-surrogate gradient (PPOAgent.cs:232-326), tanh backward: computed by BOTH halves (each needs
+    //      g3 for its columns of G2); half 0 keeps the actor-side sums, half 1 the critic side and stages [g3 | gv]
     float g3[kAct] = {0.f, 0.f, 0.f, 0.f}, gv = 0.f;
-    if (valid) {
-      const float adv = p.advantages[gs];
+    if (epi) {
+      // the exp / division heavy per-dimension part is split inside the warp: lanes 0..15 take action dimensions 0 and 1 of
+      // their sample, lanes 16..31 dimensions 2 and 3 of the same sample; one shuffle brings the four results together
+      const bool live = s_loc < nvalid;
+      const int k0 = (lane >> 4) * 2;
+      float part[2] = {0.f, 0.f};
       bool skip = false;
+      if (live) {
+        const float adv = p.advantages[gs];
 #pragma unroll
-      for (int k = 0; k < kAct; k++) {
-        const float a = p.actions[(size_t)gs * kAct + k];
-        const float lp_old = p.old_logp[(size_t)gs * kAct + k];
-        const float lp = tc_log_prob(mu[k], gc.stdv, a, gc.neg_log_std, gc.log_sqrt_2pi);
-        const float ratio = expf(lp - lp_old);
-        const float clipped = ratio >= gc.upper ? gc.upper : (ratio <= gc.lower ? gc.lower : ratio);
-        const float cra = clipped * adv, ra = ratio * adv;
-        const float partA = (ra <= cra ? 1.0f : 0.0f) * adv;
-        const float partB = (cra < ra ? 1.0f : 0.0f) * adv;
-        const float partC = (ratio >= gc.lower && ratio <= gc.upper) ? 1.0f : 0.0f;
-        float dclip = (partA + partB * partC) * -1.0f;
-        const float pold = expf(lp_old);
-        if (pold == 0.0f) skip = true;
-        dclip = dclip / pold;
-        const float dmean = expf(lp) * ((a - mu[k]) / gc.variance);
-        g3[k] = (dmean * dclip) / p.batch_size;
+        for (int d = 0; d < 2; d++) {
+          const int k = k0 + d;
+          const float muk = d == 0 ? (k0 == 0 ? mu[0] : mu[2]) : (k0 == 0 ? mu[1] : mu[3]);
+          const float a = p.actions[(size_t)gs * kAct + k];
+          const float lp_old = p.old_logp[(size_t)gs * kAct + k];
+          const float lp = tc_log_prob(muk, gc.stdv, a, gc.neg_log_std, gc.log_sqrt_2pi);
+          const float ratio = expf(lp - lp_old);
+          const float clipped = ratio >= gc.upper ? gc.upper : (ratio <= gc.lower ? gc.lower : ratio);
+          const float cra = clipped * adv, ra = ratio * adv;
+          const float partA = (ra <= cra ? 1.0f : 0.0f) * adv;
+          const float partB = (cra < ra ? 1.0f : 0.0f) * adv;
+          const float partC = (ratio >= gc.lower && ratio <= gc.upper) ? 1.0f : 0.0f;
+          float dclip = (partA + partB * partC) * -1.0f;
+          const float pold = expf(lp_old);
+          if (pold == 0.0f) skip = true;
+          dclip = dclip / pold;
+          const float dmean = expf(lp) * ((a - muk) / gc.variance);
+          part[d] = (dmean * dclip) / p.batch_size;
+        }
       }
-      gv = (2.0f * (value - p.returns[gs])) / p.batch_size;
-      if (skip) {
+      const float o0 = __shfl_xor_sync(0xFFFFFFFFu, part[0], 16), o1 = __shfl_xor_sync(0xFFFFFFFFu, part[1], 16);
+      const int other_skip = __shfl_xor_sync(0xFFFFFFFFu, skip ? 1 : 0, 16);  // (unconditional: every lane takes part)
+      skip = skip || other_skip != 0;
+      g3[0] = k0 == 0 ? part[0] : o0;
+      g3[1] = k0 == 0 ? part[1] : o1;
+      g3[2] = k0 == 0 ? o0 : part[0];
+      g3[3] = k0 == 0 ? o1 : part[1];
+      if (valid) {
+        if (half == 1) gv = (2.0f * (value - p.returns[gs])) / p.batch_size;
+        if (skip) {
+#pragma unroll
+          for (int k = 0; k < kAct; k++) g3[k] = 0.f;
+          gv = 0.f;
+          if (half == 0) skipped += 1.0f;
+        } else if (half == 0) {
+          lossA += (((g3[0] + g3[1]) + g3[2]) + g3[3]) / (float)kAct;
+        } else {
+          lossV += gv;
+        }
+#pragma unroll
+        for (int k = 0; k < kAct; k++) {
+          g3[k] = g3[k] * (1.0f - (mu[k] * mu[k]));  // TanhLayer.FeedBack
+          if (half == 0) db3_acc[k] += g3[k];
+        }
+        if (half == 1) dbc2_acc += gv;
+      } else {
 #pragma unroll
         for (int k = 0; k < kAct; k++) g3[k] = 0.f;
-        gv = 0.f;
-        skipped += 1.0f;
-      } else {
-        lossV += gv;
-        lossA += (((g3[0] + g3[1]) + g3[2]) + g3[3]) / (float)kAct;
       }
-#pragma unroll
-      for (int k = 0; k < kAct; k++) {
-        g3[k] = g3[k] * (1.0f - (mu[k] * mu[k]));  // TanhLayer.FeedBack
-        db3_acc[k] += g3[k];
-      }
-      dbc2_acc += gv;
     }
-    if (is_sample) {
+    if (is_sample && half == 1) {
       const float u[8] = {g3[0], g3[1], g3[2], g3[3], gv, 0.f, 0.f, 0.f};
       store_unit(S.g3v_hi, S.g3v_lo, s_loc, 0, u);
     }
@@ -490,29 +585,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     // ---- P5: [C1|A2]^T x [g3|gv]  (accumulates dWc2 and dW3 over all tiles)
     if (issuer) {
-      issue_chain(tmem + kColDW3, 128, 8, S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, kMnMajor, kS, S.g3v_hi, S.g3v_lo, kMnMajor, kS, 8, any_tile);
+      issue_range(S.mma, kChainDW3, kChainB2, tmem, any_tile);
       tc::mma_commit(&S.mbar);
     }
-    // dL/dz2 = (W3^T g3) * leaky'(z2) in registers while the tensor core runs (sum over k from 0, Matrix.Multiply order)
-    if (epi) tc::mbar_wait(&S.mbar, phase);
+    if (epi) tc::mbar_wait(&S.mbar, phase);  // G2 overwrites A2, which this MMA reads
     phase ^= 1;
     __syncwarp();
     tc::fence_after_thread_sync();
-    if (epi)
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 8) {
-      float v[8];
+    // dL/dz2 = (W3^T g3) * leaky'(z2) for the half's 32 columns (sum over k from 0, Matrix.Multiply order)
+    if (epi) {
+      const int c0 = half * 32;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int o = c + j;
-        float sum = 0.f;
-        sum = fmaf(S.w3[0 * kHid + o], g3[0], sum);
-        sum = fmaf(S.w3[1 * kHid + o], g3[1], sum);
-        sum = fmaf(S.w3[2 * kHid + o], g3[2], sum);
-        sum = fmaf(S.w3[3 * kHid + o], g3[3], sum);
-        v[j] = sum * (((maskA2 >> o) & 1ull) ? 0.2f : 1.0f);
+      for (int c = 0; c < 32; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int o = c0 + c + j;
+          float sum = 0.f;
+          sum = fmaf(S.w3[0 * kHid + o], g3[0], sum);
+          sum = fmaf(S.w3[1 * kHid + o], g3[1], sum);
+          sum = fmaf(S.w3[2 * kHid + o], g3[2], sum);
+          sum = fmaf(S.w3[3 * kHid + o], g3[3], sum);
+          v[j] = sum * (((maskA2 >> (c + j)) & 1u) ? 0.2f : 1.0f);
+        }
+        if (is_sample) store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c0 + c, v);  // G2 overwrites A2
       }
-      if (is_sample) store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c, v);  // G2 overwrites A2
     }
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
@@ -521,9 +618,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     // ---- P6: dL/dA1 = G2 x W2 ; dW2 += G2^T x A1 ; dB2 += G2^T x [X|1]
     if (issuer) {
-      issue_chain(tmem + kColB2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kKMajor, kS, S.w2_hi, S.w2_lo, kMnMajor, kHid, 8, false);
-      issue_chain(tmem + kColDW2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.act_hi, S.act_lo, kMnMajor, kS, 8, any_tile);
-      issue_chain(tmem + kColDB2, 64, 16, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, any_tile);
+      issue_range(S.mma, kChainB2, kChainDW1, tmem, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -531,24 +626,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncwarp();
     tc::fence_after_thread_sync();
 
-    // ---- P7: G1 = dL/dA1 * leaky'(z1) ; Gc1 = (Wc2^T gv) * leaky'(zc1)  -> overwrite A1 | C1
-    if (epi)
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 16) {
-      float v[16], w[16];
-      tc::tmem_ld_x16(tmem_warp + kColB2 + c, v);
-      tc::tmem_ld_wait();
+    // ---- P7: half 0: G1 = dL/dA1 * leaky'(z1) -> overwrites A1; half 1: Gc1 = (Wc2^T gv) * leaky'(zc1) -> overwrites C1
+    if (epi) {
+      float* hi_t = S.act_hi + half * 2 * kBlk;
+      float* lo_t = S.act_lo + half * 2 * kBlk;
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int i = c + j;
-        v[j] = v[j] * (((maskA1 >> i) & 1ull) ? 0.2f : 1.0f);
-        w[j] = (0.0f + S.wc2[i] * gv) * (((maskC1 >> i) & 1ull) ? 0.2f : 1.0f);
-      }
-      if (is_sample) {
-        store_unit(S.act_hi, S.act_lo, s_loc, c, v);
-        store_unit(S.act_hi, S.act_lo, s_loc, c + 8, v + 8);
-        store_unit(S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, s_loc, c, w);
-        store_unit(S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, s_loc, c + 8, w + 8);
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        if (half == 0) {
+          tc::tmem_ld_x32(tmem_warp + kColB2 + c, v);
+          tc::tmem_ld_wait();
+        }
+        const unsigned m = mask1[c >> 5];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float slope = ((m >> j) & 1u) ? 0.2f : 1.0f;
+          v[j] = (half == 0 ? v[j] : (0.0f + S.wc2[c + j] * gv)) * slope;
+        }
+        if (is_sample) {
+#pragma unroll
+          for (int u = 0; u < 32; u += 8) store_unit(hi_t, lo_t, s_loc, c + u, v + u);
+        }
       }
     }
     tc::fence_proxy_async_smem();
@@ -558,7 +656,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     // ---- P8: [G1|Gc1]^T x [X|1]  (accumulates dW1, db1, dWc1, dbc1)
     if (issuer) {
-      issue_chain(tmem + kColDW1, 128, 16, S.act_hi, S.act_lo, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, any_tile);
+      issue_range(S.mma, kChainDW1, kMmaEntries, tmem, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);  // the next tile overwrites XT and ACT
@@ -569,11 +667,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   }
 
   if (grad) {
-    // ---- per-CTA partial gradient straight out of TMEM (flat parameter layout of mlp.cuh)
+    // ---- per-CTA partial gradient straight out of TMEM (flat parameter layout of mlp.cuh), warps 0..3
     float* out = p.partials + (size_t)blockIdx.x * kGradFloats;
     if (!any_tile) {
       for (int i = tid; i < kGradFloats; i += kTcThreads) out[i] = 0.f;
-    } else if (epi) {
+    } else if (warp < 4) {
       // dW2 / db2: M = 64 accumulators, row o lives in the sample threads' lanes
 #pragma unroll 1
       for (int c = 0; c < 64; c += 16) {
@@ -619,9 +717,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     for (int pass = 0; pass < 8; pass++) {
       const float mine = pass < 4 ? db3_acc[pass] : pass == 4 ? dbc2_acc : pass == 5 ? lossV : pass == 6 ? lossA : skipped;
       S.red[tid] = mine;
-      if (tid < 96) S.red[kTcThreads + tid] = 0.f;
+      if (tid < 512 - kTcThreads) S.red[kTcThreads + tid] = 0.f;
       __syncthreads();
-      for (int w = 128; w > 0; w >>= 1) {
+      for (int w = 256; w > 0; w >>= 1) {
         if (tid < w) S.red[tid] += S.red[tid + w];
         __syncthreads();
       }
