@@ -1233,7 +1233,7 @@ cudaError_t upload_scene_constants(const float* init_state92, const FloorConst* 
 // per walker with CTA-level work compaction (the throughput kernel)
 bool physics_lanes_supported(int variant) {
   switch (variant) {
-    case 1: case 2: case 4: case 8: case 16: case 104: case 108: case 116: case 1001: return true;
+    case 1: case 2: case 4: case 8: case 16: case 32: case 104: case 108: case 116: case 1001: return true;
     default: return false;
   }
 }
@@ -1245,6 +1245,7 @@ cudaError_t launch_physics(const PhysicsParams& p, int variant, bool trace, cuda
     case 4: return pl::launch_l<4, 2>(p, trace, stream);
     case 8: return pl::launch_l<8, 2>(p, trace, stream);
     case 16: return pl::launch_l<16, 2>(p, trace, stream);
+    case 32: return pl::launch_l<32, 2>(p, trace, stream);
     case 104: return pl::launch_l<4, 1>(p, trace, stream);
     case 108: return pl::launch_l<8, 1>(p, trace, stream);
     case 116: return pl::launch_l<16, 1>(p, trace, stream);
