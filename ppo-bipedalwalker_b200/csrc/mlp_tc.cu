@@ -371,23 +371,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   bool any_tile = false;
 
   const int ntiles = (p.n + kS - 1) / kS;
+  // global inputs of a tile are fetched into registers one tile AHEAD (their latency hides behind the previous tile's pipeline):
+  // the [X | 1] elements this thread stages (4 of the 64 x 16) and, for the gradient, its sample's two action dimensions
+  constexpr int kXPer = (kS * 16 + kTcThreads - 1) / kTcThreads;
+  float x_next[kXPer];
+  float a_next[2] = {0.f, 0.f}, lp_next[2] = {0.f, 0.f}, adv_next = 0.f, ret_next = 0.f;
+  auto prefetch = [&](int tile) {
+    const int s0 = tile * kS;
+    const int nvalid = tile < ntiles ? min(kS, p.n - s0) : 0;
+#pragma unroll
+    for (int q = 0; q < kXPer; q++) {
+      const int i = tid + q * kTcThreads;
+      const int s = i >> 4, f = i & 15;
+      float v = 0.f;
+      if (i < kS * 16 && s < nvalid) v = (f < kIn) ? p.states[(size_t)(s0 + s) * kIn + f] : (f == kIn ? 1.0f : 0.f);
+      x_next[q] = v;
+    }
+    if (grad && epi && s_loc < nvalid) {
+      const size_t g = (size_t)(s0 + s_loc);
+      const int k0 = (lane >> 4) * 2;
+      const float2 a2 = *reinterpret_cast<const float2*>(p.actions + g * kAct + k0);
+      const float2 l2 = *reinterpret_cast<const float2*>(p.old_logp + g * kAct + k0);
+      a_next[0] = a2.x;
+      a_next[1] = a2.y;
+      lp_next[0] = l2.x;
+      lp_next[1] = l2.y;
+      adv_next = p.advantages[g];
+      ret_next = p.returns[g];
+    }
+  };
+  prefetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int s0 = tile * kS;
     const int nvalid = min(kS, p.n - s0);
     const int gs = s0 + s_loc;
     const bool valid = is_sample && s_loc < nvalid;
 
-    // ---- P0: stage [X | 1] (coalesced global read, 16 features per sample; ones column = bias input)
-    for (int i = tid; i < kS * 16; i += kTcThreads) {
-      const int s = i >> 4, f = i & 15;
-      float v = 0.f;
-      if (s < nvalid) v = (f < kIn) ? p.states[(size_t)(s0 + s) * kIn + f] : (f == kIn ? 1.0f : 0.f);
-      float h, l;
-      tc::split_tf32(v, h, l);
-      const int off = tile_off_b32(s, f, kS);
-      S.xt_hi[off] = h;
-      S.xt_lo[off] = l;
+    // ---- P0: stage [X | 1] (16 features per sample; ones column = bias input) from the prefetched registers
+#pragma unroll
+    for (int q = 0; q < kXPer; q++) {
+      const int i = tid + q * kTcThreads;
+      if (i < kS * 16) {
+        float h, l;
+        tc::split_tf32(x_next[q], h, l);
+        const int off = tile_off_b32(i >> 4, i & 15, kS);
+        S.xt_hi[off] = h;
+        S.xt_lo[off] = l;
+      }
     }
+    const float a_cur[2] = {a_next[0], a_next[1]}, lp_cur[2] = {lp_next[0], lp_next[1]};
+    const float adv_cur = adv_next, ret_cur = ret_next;
+    prefetch(tile + gridDim.x);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     __syncthreads();
@@ -522,13 +556,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       float part[2] = {0.f, 0.f};
       bool skip = false;
       if (live) {
-        const float adv = p.advantages[gs];
+        const float adv = adv_cur;
 #pragma unroll
         for (int d = 0; d < 2; d++) {
-          const int k = k0 + d;
           const float muk = d == 0 ? (k0 == 0 ? mu[0] : mu[2]) : (k0 == 0 ? mu[1] : mu[3]);
-          const float a = p.actions[(size_t)gs * kAct + k];
-          const float lp_old = p.old_logp[(size_t)gs * kAct + k];
+          const float a = a_cur[d];
+          const float lp_old = lp_cur[d];
           const float lp = tc_log_prob(muk, gc.stdv, a, gc.neg_log_std, gc.log_sqrt_2pi);
           const float ratio = expf(lp - lp_old);
           const float clipped = ratio >= gc.upper ? gc.upper : (ratio <= gc.lower ? gc.lower : ratio);
@@ -552,7 +585,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       g3[2] = k0 == 0 ? o0 : part[0];
       g3[3] = k0 == 0 ? o1 : part[1];
       if (valid) {
-        if (half == 1) gv = (2.0f * (value - p.returns[gs])) / p.batch_size;
+        if (half == 1) gv = (2.0f * (value - ret_cur)) / p.batch_size;
         if (skip) {
 #pragma unroll
           for (int k = 0; k < kAct; k++) g3[k] = 0.f;
