@@ -64,6 +64,21 @@ public static class Wb
     [DllImport(Lib)] public static extern int wb_adam_step(IntPtr policy);
     [DllImport(Lib)] public static extern int wb_returns_advantages(IntPtr policy, int n, float[] rewards, float[] values, float[] returns, float[] advantages);
 
+    // kernel choice and the device-resident lockstep loop (device pointers: IntPtr obtained from the CUDA allocator of the host process)
+    [DllImport(Lib)] public static extern int wb_env_set_variant(IntPtr env, int lanesPerWalker);   // 0 = chosen from the batch size
+    [DllImport(Lib)] public static extern int wb_env_get_variant(IntPtr env, out int lanesPerWalker);
+    [DllImport(Lib)] public static extern int wb_policy_set_variant(IntPtr policy, int variant);     // 0 tcgen05, 1 fp32 CUDA cores
+    [DllImport(Lib)] public static extern int wb_env_step_dev(IntPtr env, IntPtr actionsDev, float deltaTime, int autoReset, IntPtr obsDev, IntPtr rewardDev, IntPtr doneDev);
+    [DllImport(Lib)] public static extern int wb_policy_act_dev(IntPtr policy, int n, IntPtr statesDev, ulong seed, ulong step, IntPtr actionsDev, IntPtr logpDev,
+                                                               IntPtr meanDev, IntPtr valueDev);               // SampleActions + GetValueEstimate, N walkers
+    [DllImport(Lib)] public static extern int wb_segment_returns_dev(IntPtr policy, int nEnvs, int horizon, IntPtr rewardsDev, IntPtr valuesDev, IntPtr donesDev,
+                                                                    IntPtr returnsDev, IntPtr advantagesDev); // MonteCarloReturn / GAE per episode fragment
+    [DllImport(Lib)] public static extern int wb_gather_minibatch_dev(IntPtr policy, int batch, IntPtr indexDev, IntPtr statesPool, IntPtr actionsPool, IntPtr logpPool,
+                                                                     IntPtr advantagesPool, IntPtr returnsPool, IntPtr statesOut, IntPtr actionsOut, IntPtr logpOut,
+                                                                     IntPtr advantagesOut, IntPtr returnsOut);   // CreateBatches
+    [DllImport(Lib)] public static extern int wb_ppo_grad_dev(IntPtr policy, int n, IntPtr statesDev, IntPtr actionsDev, IntPtr oldLogpDev, IntPtr advantagesDev, IntPtr returnsDev);
+    [DllImport(Lib)] public static extern int wb_policy_grad_buffer(IntPtr policy, out IntPtr devPtr, out int nFloats);   // for the NCCL all-reduce
+
     /// The reference never surfaces hot-path errors: it logs and continues (RigidBody.cs:91-94). Same here.
     public static bool Ok(int status, string what)
     {
