@@ -851,7 +851,7 @@ static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t str
 // and in a decorrelated rollout the expensive branches are rare per walker yet almost always present in some lane: a leg
 // pair's AABBs overlap 85 % of the time but SAT finds a collision in only ~10 % of the substeps, the floor is touched in ~5 %,
 // a joint needs correcting in ~20 % (profiles/physics_r1_hotspots.md: 31 % of the executed lane-slots did useful work).
-// Here the CTA (128 walkers) advances in lockstep PHASES, and each phase has two stages:
+// Here a CTA of kE walkers (256 by default) advances in lockstep PHASES, and each phase has two stages:
 //   stage 1  every thread, for ITS walker: the cheap, common part -- integrate the body; for a leg pair test the separating
 //            axis that separated this pair last time (temporal coherence; any order of the axis tests gives the reference's
 //            result: if one axis separates, SATCollision.IsColliding is false whatever the others say), then the AABBs; for
@@ -866,9 +866,11 @@ static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t str
 namespace pc {
 using namespace pl;
 
-constexpr int kE = 128;  // walkers (= threads) per CTA
-using EV = Env<1, kE>;
-
+// kE walkers (= threads) share one queue and advance in lockstep.  Measured at 262144 walkers (ms per env-step): kE = 32 (ONE
+// WARP per CTA, rounds separated by __syncwarp only, no block barrier anywhere) 8.86 -- sparse per-warp queues execute the
+// expensive stage once per warp however few items it has; 64: 7.35; 128: 5.93; 256: 5.45 (default); 512: 6.06 (one CTA per SM:
+// nothing overlaps its barriers).  Aggregation beats barrier cost up to the point where CTAs stop overlapping each other.
+template <int kE>
 struct Shared {
   float state[(kV2Count * 2 + kFCount) * kE];
   float mat[6 * kE];            // im_w, ii_pole, e_ww, mu_ww, e_wf, mu_wf per walker (stage 2 works on other walkers)
@@ -877,8 +879,16 @@ struct Shared {
   unsigned short queue[2 * kE];
   int count[2];  // ping-pong: the counter of the next round is cleared while the current one drains
 };
+template <int kE> __device__ __forceinline__ void scope_sync() {
+  if (kE == 32) __syncwarp(); else __syncthreads();
+}
+template <int kE> __device__ __forceinline__ bool scope_any(bool pred) {
+  if (kE == 32) return __any_sync(kFull, pred) != 0;
+  return __syncthreads_or(pred) != 0;
+}
 
-__device__ __forceinline__ void env_for_column(EV& e, Shared& S, int col, bool live) {
+template <int kE>
+__device__ __forceinline__ void env_for_column(Env<1, kE>& e, Shared<kE>& S, int col, bool live) {
   e.v2 = reinterpret_cast<float2*>(S.state) + col;
   e.f = S.state + kV2Count * kE * 2 + col;
   e.fl = &S.floor;
@@ -896,7 +906,8 @@ __device__ __forceinline__ void env_for_column(EV& e, Shared& S, int col, bool l
 }
 
 // queue push: one shared-memory atomic per warp
-__device__ __forceinline__ void push(Shared& S, int parity, bool want, int item) {
+template <int kE>
+__device__ __forceinline__ void push(Shared<kE>& S, int parity, bool want, int item) {
   const unsigned m = __ballot_sync(kFull, want);
   if (m == 0) return;
   const int lane = threadIdx.x & 31;
@@ -908,6 +919,7 @@ __device__ __forceinline__ void push(Shared& S, int parity, bool want, int item)
 
 // stage 1 of a leg pair: true when the pair needs the full narrow phase.  Tests the cached axis first (a separating axis
 // settles the pair: no collision, nothing else to do), then the bounding boxes.
+template <class EV>
 __device__ __noinline__ bool pole_pair_needs_work(const EV& e, int A, int B, int cached) {
   float2 PA[6], PB[6];
 #pragma unroll
@@ -933,6 +945,7 @@ __device__ __noinline__ bool pole_pair_needs_work(const EV& e, int A, int B, int
 }
 
 // stage 1 of a floor pair: bounding boxes + the Collided latch (RigidBody.cs:73-76)
+template <class EV>
 __device__ __noinline__ bool floor_pair_needs_work(EV& e, int A) {
   float2 PA[6];
 #pragma unroll
@@ -945,6 +958,7 @@ __device__ __noinline__ bool floor_pair_needs_work(EV& e, int A) {
 }
 
 // RigidBody.StepLinearVelocity / StepAngularVelocity / Skeleton.Move / Rotate of one body (the first half of body_step)
+template <class EV>
 __device__ __noinline__ void integrate_body(const EV& e, int b, float dt) {
   float2 v = V2(e, kV2Vel + b);
   v = vadd(v, vmul(mk2(0.0f, 980.0f), dt));
@@ -980,11 +994,11 @@ enum { kItemPole = 0, kItemFloor = 1, kItemJoint = 2 };
 
 // stage 2: the queued items, densely, kG lanes per item (the lanes split the SAT axes and the vertices of the moves exactly
 // like the L > 1 layouts of the plain kernel; with ~15-20 % of the walkers queued per round this keeps most warps of the CTA
-// busy and roughly halves the latency of the round).  Item = walker column | payload << 7.
+// busy and roughly halves the latency of the round).  Item = walker column | payload << 10.
 constexpr int kG = 2;
-using EVG = Env<kG, kE>;
 
-__device__ __forceinline__ void group_env_for_column(EVG& e, Shared& S, int col, bool live) {
+template <int kE>
+__device__ __forceinline__ void group_env_for_column(Env<kG, kE>& e, Shared<kE>& S, int col, bool live) {
   e.v2 = reinterpret_cast<float2*>(S.state) + col;
   e.f = S.state + kV2Count * kE * 2 + col;
   e.fl = &S.floor;
@@ -1001,8 +1015,9 @@ __device__ __forceinline__ void group_env_for_column(EVG& e, Shared& S, int col,
   e.mu_wf = S.mat[5 * kE + col];
 }
 
-template <int KIND>
-__device__ __noinline__ void drain(Shared& S, int parity) {
+template <int KIND, int kE>
+__device__ __noinline__ void drain(Shared<kE>& S, int parity) {
+  using EVG = Env<kG, kE>;
   const int count = S.count[parity];
   const int warp_base = (threadIdx.x >> 5) * (32 / kG), lane = threadIdx.x & 31;
 #pragma unroll 1
@@ -1010,7 +1025,7 @@ __device__ __noinline__ void drain(Shared& S, int parity) {
     const int slot = base + lane / kG;
     const bool valid = slot < count;
     const int item = valid ? S.queue[slot] : 0;
-    const int col = item & 127, payload = item >> 7;
+    const int col = item & 1023, payload = item >> 10;
     EVG q;
     group_env_for_column(q, S, col, valid);
     if (KIND == kItemPole) {
@@ -1028,9 +1043,11 @@ __device__ __noinline__ void drain(Shared& S, int parity) {
   }
 }
 
-__global__ void __launch_bounds__(kE, 4) physics_compact_kernel(const PhysicsParams p) {
+template <int kE>
+__global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const PhysicsParams p) {
+  using EV = Env<1, kE>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Shared& S = *reinterpret_cast<Shared*>(smem_raw);
+  Shared<kE>& S = *reinterpret_cast<Shared<kE>*>(smem_raw);
   const int tid = threadIdx.x;
   const int env0 = blockIdx.x * kE;
   const int env = env0 + tid;
@@ -1056,6 +1073,7 @@ __global__ void __launch_bounds__(kE, 4) physics_compact_kernel(const PhysicsPar
 #pragma unroll
   for (int s = 0; s < 4; s++) S.axis[s * kE + tid] = 0;
   if (tid == 0) S.count[0] = S.count[1] = 0;
+  scope_sync<kE>();  // the floor constants / counters written above are read by every thread of the scope
   EV e;
   env_for_column(e, S, tid, live);
   V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
@@ -1101,8 +1119,8 @@ __global__ void __launch_bounds__(kE, 4) physics_compact_kernel(const PhysicsPar
     // which floor sub-phases this CTA needs at all (the list order only changes at a reset, never inside the sweep)
     // padding threads (env >= n) sweep a scratch copy of the initial walker like everybody else -- no thread of the CTA ever
     // leaves the lockstep -- and simply never store anything to global memory
-    const bool any_first = __syncthreads_or(floor_first) != 0;
-    const bool any_last = __syncthreads_or(!floor_first) != 0;
+    const bool any_first = scope_any<kE>(floor_first);
+    const bool any_last = scope_any<kE>(!floor_first);
 
     auto joint_gap_active = [&](int k) {
       const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
@@ -1113,23 +1131,23 @@ __global__ void __launch_bounds__(kE, 4) physics_compact_kernel(const PhysicsPar
     // one queue round: (stage 1 already pushed) barrier, drain, barrier; the other counter is cleared in between
     int parity = 0;
     auto round = [&](auto drain_fn) {
-      __syncthreads();
+      scope_sync<kE>();
       if (tid == 0) S.count[parity ^ 1] = 0;
       drain_fn();
-      __syncthreads();
+      scope_sync<kE>();
       parity ^= 1;
     };
 
 #pragma unroll 1
     for (int it = 0; it < p.iterations; it++) {
       // ---- joints in creation order; (Body,RLU) and (LLU,LLL) touch disjoint bodies and share a round
-      push(S, parity, joint_gap_active(0), tid | (0 << 7));
-      round([&] { drain<kItemJoint>(S, parity); });
-      push(S, parity, joint_gap_active(1), tid | (1 << 7));
-      push(S, parity, joint_gap_active(2), tid | (2 << 7));
-      round([&] { drain<kItemJoint>(S, parity); });
-      push(S, parity, joint_gap_active(3), tid | (3 << 7));
-      round([&] { drain<kItemJoint>(S, parity); });
+      push(S, parity, joint_gap_active(0), tid | (0 << 10));
+      round([&] { drain<kItemJoint, kE>(S, parity); });
+      push(S, parity, joint_gap_active(1), tid | (1 << 10));
+      push(S, parity, joint_gap_active(2), tid | (2 << 10));
+      round([&] { drain<kItemJoint, kE>(S, parity); });
+      push(S, parity, joint_gap_active(3), tid | (3 << 10));
+      round([&] { drain<kItemJoint, kE>(S, parity); });
       // ---- body sweep: {LLL, RLL}, {LLU, RLU}, {Body}; per body [floor if floor-first] [leg partner] [floor if floor-last]
 #pragma unroll 1
       for (int ph = 0; ph < 3; ph++) {
@@ -1139,22 +1157,22 @@ __global__ void __launch_bounds__(kE, 4) physics_compact_kernel(const PhysicsPar
         integrate_body(e, b0, dt);
         if (nb == 2) integrate_body(e, b1, dt);
         if (ph == 2) {
-          push(S, parity, floor_pair_needs_work(e, BODY), tid | (BODY << 7));
-          round([&] { drain<kItemFloor>(S, parity); });
+          push(S, parity, floor_pair_needs_work(e, BODY), tid | (BODY << 10));
+          round([&] { drain<kItemFloor, kE>(S, parity); });
           continue;
         }
         if (any_first) {
-          push(S, parity, floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 7));
-          push(S, parity, floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 7));
-          round([&] { drain<kItemFloor>(S, parity); });
+          push(S, parity, floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 10));
+          push(S, parity, floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 10));
+          round([&] { drain<kItemFloor, kE>(S, parity); });
         }
-        push(S, parity, pole_pair_needs_work(e, b0, partner_of(b0), S.axis[pair_slot(b0) * kE + tid]), tid | (b0 << 7));
-        push(S, parity, pole_pair_needs_work(e, b1, partner_of(b1), S.axis[pair_slot(b1) * kE + tid]), tid | (b1 << 7));
-        round([&] { drain<kItemPole>(S, parity); });
+        push(S, parity, pole_pair_needs_work(e, b0, partner_of(b0), S.axis[pair_slot(b0) * kE + tid]), tid | (b0 << 10));
+        push(S, parity, pole_pair_needs_work(e, b1, partner_of(b1), S.axis[pair_slot(b1) * kE + tid]), tid | (b1 << 10));
+        round([&] { drain<kItemPole, kE>(S, parity); });
         if (any_last) {
-          push(S, parity, !floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 7));
-          push(S, parity, !floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 7));
-          round([&] { drain<kItemFloor>(S, parity); });
+          push(S, parity, !floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 10));
+          push(S, parity, !floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 10));
+          round([&] { drain<kItemFloor, kE>(S, parity); });
         }
       }
     }
@@ -1203,14 +1221,15 @@ __global__ void __launch_bounds__(kE, 4) physics_compact_kernel(const PhysicsPar
   }
 }
 
+template <int kE>
 static cudaError_t launch_compact(const PhysicsParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(physics_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    cudaError_t e = cudaFuncSetAttribute(physics_compact_kernel<kE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared<kE>));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  physics_compact_kernel<<<(p.n + kE - 1) / kE, kE, sizeof(Shared), stream>>>(p);
+  physics_compact_kernel<kE><<<(p.n + kE - 1) / kE, kE, sizeof(Shared<kE>), stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -1230,10 +1249,11 @@ cudaError_t upload_scene_constants(const float* init_state92, const FloorConst* 
 
 // variant code = lanes per environment (1, 2, 4, 8, 16; for >= 2 the lanes split by leg first), 100 + lanes (4, 8, 16) for
 // the measured-for-comparison layout without the leg split (all lanes of a walker work on one pair), or 1001 = one thread
-// per walker with CTA-level work compaction (the throughput kernel)
+// per walker with work compaction over a lockstep scope of 256 walkers (the throughput kernel; 1002 / 1003: scope of one warp /
+// of 128 walkers, kept for comparison)
 bool physics_lanes_supported(int variant) {
   switch (variant) {
-    case 1: case 2: case 4: case 8: case 16: case 32: case 104: case 108: case 116: case 1001: return true;
+    case 1: case 2: case 4: case 8: case 16: case 32: case 104: case 108: case 116: case 1001: case 1002: case 1003: return true;
     default: return false;
   }
 }
@@ -1249,7 +1269,10 @@ cudaError_t launch_physics(const PhysicsParams& p, int variant, bool trace, cuda
     case 104: return pl::launch_l<4, 1>(p, trace, stream);
     case 108: return pl::launch_l<8, 1>(p, trace, stream);
     case 116: return pl::launch_l<16, 1>(p, trace, stream);
-    case 1001: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact(p, stream);  // (the trace hook uses the plain kernel)
+    // compacting kernels (the trace hook uses the plain kernel): lockstep scope of 256 walkers (default), one warp, 128 walkers
+    case 1001: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<256>(p, stream);
+    case 1002: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<32>(p, stream);
+    case 1003: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<128>(p, stream);
     default: return cudaErrorInvalidValue;
   }
 }

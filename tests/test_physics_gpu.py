@@ -205,7 +205,7 @@ def test_rotation_coefficients_match_libm_rounded_to_float(gpu, O, mode):
         assert bad_c == 0 and bad_s == 0
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 104, 108, 116, 1001])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32, 104, 108, 116, 1001, 1002, 1003])
 def test_kernel_variants_bit_exact(gpu, O, lanes):
     """Both thread mappings (two envs per warp / one env per warp) against the oracle, traces included."""
     n = 40
