@@ -55,3 +55,36 @@ def test_bench_our_arm_refuses_to_run_without_a_gpu():
         pytest.skip("a CUDA device is present")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode != 0  # no CPU fallback, no silent oracle substitution
+
+
+def test_hyperparameter_json_roundtrip_and_validation(wb, tmp_path):
+    """Hyperparameters.SerializeJson / DeserializeJson / ValidateHyperparameterValues (Hyperparameters.cs:124-217)."""
+    import json
+    s = wb.Settings(Iterations=25, BatchSize=128, Gamma=0.97, UseGAE=True, FilePath="/data")
+    path = tmp_path / "Data" / "settings.json"
+    wb.SerializeJson(s, str(path))
+    doc = json.loads(path.read_text())
+    assert list(doc)[:6] == ["GameSpeed", "CollectData", "SaveWeights", "Iterations", "MaxTimesteps", "RoughFloor"]  # the reference's member order
+    assert doc["CriticNeuralNetwork"] == "Input |64| (LeakyReLU) |1| Output" and doc["LogStandardDeviation"] == -1.0
+    back = wb.DeserializeJson(str(path))
+    assert back == s
+    hp = back.to_hyperparams()
+    assert (hp.iterations, hp.batch_size, hp.use_gae) == (25, 128, 1) and abs(hp.gamma - 0.97) < 1e-7
+    # out-of-range value: logged, current settings kept (the reference logs and returns, :141-185)
+    logged = []
+    doc["Iterations"] = 200
+    path.write_text(json.dumps(doc))
+    kept = wb.DeserializeJson(str(path), current=s, log=logged.append)
+    assert kept is s and "Invalid iterations count" in logged[0]
+    # the boundary semantics are the reference's: Beta1 == 1 and Gamma == 1 are accepted, Epochs == 50 is not
+    doc.update(Iterations=199, Beta1=1.0, Gamma=1.0)
+    path.write_text(json.dumps(doc))
+    assert wb.DeserializeJson(str(path)).Beta1 == 1.0
+    doc["Epochs"] = 50
+    path.write_text(json.dumps(doc))
+    assert wb.DeserializeJson(str(path), current=s) is s
+    # malformed document / missing members (System.Text.Json leaves 0 / false / null, which then fails validation)
+    path.write_text("{ not json")
+    assert wb.DeserializeJson(str(path), current=s, log=logged.append) is s and "JSON deserializer error" in logged[-1]
+    path.write_text(json.dumps({"Iterations": 50}))
+    assert wb.DeserializeJson(str(path), current=s) is s
