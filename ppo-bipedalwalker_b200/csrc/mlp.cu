@@ -543,11 +543,14 @@ int mlp_grid_for(int n, int sm_count) {
 }
 
 cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  // opt in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute (a process may drive several GPUs)
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem));
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   GradConsts gc;
   gc.stdv = expf(p.log_std);                       // PPOAgent.GetStandardDeviations, PPOAgent.cs:367-378

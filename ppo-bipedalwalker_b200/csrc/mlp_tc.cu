@@ -774,11 +774,14 @@ int tc_grid_for(int n, int sm_count) {
 }
 
 cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  // opt in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute (a process may drive several GPUs)
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(ppo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   TcConsts gc;
   gc.stdv = expf(p.log_std);

@@ -1223,11 +1223,14 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
 
 template <int kE>
 static cudaError_t launch_compact(const PhysicsParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  // opt in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute (a process may drive several GPUs)
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(physics_compact_kernel<kE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared<kE>));
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   physics_compact_kernel<kE><<<(p.n + kE - 1) / kE, kE, sizeof(Shared<kE>), stream>>>(p);
   return cudaGetLastError();

@@ -126,15 +126,18 @@ def test_user_material_plugin(gpu, O):
     assert_state_equal(env, ref, "custom material")
 
 
-def test_ragged_batch_sizes(gpu, O):
-    for n in (1, 7, 9):
+@pytest.mark.parametrize("variant", [0, 1, 4, 1001, 1002])
+def test_ragged_batch_sizes(gpu, O, variant):
+    """Batch sizes that leave partially filled warps / CTAs / SoA padding, for the auto-selected kernel and explicit variants."""
+    for n in (1, 7, 9, 33, 300):
         env = gpu.EnvBatch(n)
+        env.set_variant(variant)
         ref = O.EnvBatch(n)
         a = np.linspace(-1, 1, n * 4, dtype=np.float32).reshape(n, 4)
         for _ in range(3):
             env.step(a)
             ref.step(a)
-        assert_state_equal(env, ref, f"n={n}")
+        assert_state_equal(env, ref, f"n={n} variant={variant}")
 
 
 def test_nonfinite_and_out_of_range_actions_are_clipped_like_matrix_clip(gpu, O):
