@@ -182,6 +182,26 @@ def test_full_size_properties_4096_walkers(gpu):
     assert total_done > 0 and (iv[:, 1] <= 60).all()
 
 
+@pytest.mark.parametrize("variant,n,steps", [(0, 4096, 150), (1001, 4096, 150), (1, 1024, 400)])
+def test_long_rollout_at_baseline_size_bit_exact(gpu, O, variant, n, steps):
+    """BASELINE configs[1] size against the oracle itself (OpenMP over walkers): every observation, reward and done flag of a
+    long random-action rollout with many episode ends, then the complete state.  0.6 M env-steps = 30 M substeps per case."""
+    env = gpu.EnvBatch(n, floor_materials="Wood")
+    env.set_variant(variant)
+    ref = O.EnvBatch(n, floor="Wood")
+    rng = np.random.default_rng(variant + n)
+    ndone = 0
+    for t in range(steps):
+        a = rng.uniform(-1.1, 1.1, (n, 4)).astype(np.float32)
+        obs, rew, done = env.step(a)
+        robs, rrew, rdone = ref.step(a)
+        assert np.array_equal(bits(obs), bits(robs)), f"obs differ at step {t}"
+        assert np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone), f"reward/done differ at step {t}"
+        ndone += int(done.sum())
+    assert ndone > n // 4  # plenty of resets (both list orders are exercised)
+    assert_state_equal(env, ref, f"variant={variant}")
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_rotation_coefficients_match_libm_rounded_to_float(gpu, O, mode):
     """(float)cos((double)theta), (float)sin((double)theta): the polynomial fast path, the forced double-double path and
