@@ -155,6 +155,39 @@ int32_t wb_debug_rotz(int32_t n, const float* radians_host, int32_t mode, float*
  * two-intrinsic form for every float bit pattern in [first_bits, first_bits + count) and returns the number of mismatches */
 int32_t wb_debug_rcp_sqrt_check(uint32_t first_bits, uint64_t count, uint64_t* mismatches_out, uint32_t* first_bad_bits_out);
 
+/* ---- general scenes: the IObject plugin surface (Objects/IObject.cs:7-10) ----
+ * N lockstep copies of an arbitrary list of convex polygons (Square / Triangle / Hexagon / Pole / Hull ..., 3..16 vertices,
+ * Objects/RigidBodies/*.cs) with any IMaterial, static / floor flags, association ("no collide") lists (RigidBody.cs:143-152) and
+ * joints (Joint.cs), stepped by Environment.StepObjects (Environment.cs:126-143).  List order = index order.  The walker-specialised
+ * wb_env_* path covers the reference's default scene much faster; this path covers everything else the engine can be asked to do. */
+typedef struct wb_scene wb_scene;
+typedef struct {
+  int32_t n_vertices;        /* Skeleton.AddVectors: 3..16 */
+  int32_t is_static;         /* RigidBody ctor isStatic (RigidBody.cs:36-50) */
+  int32_t is_floor;          /* isFloor: an AABB overlap with it latches the other body's Collided (RigidBody.cs:75-76) */
+  int32_t material;          /* built-in id or wb_material_register */
+  uint32_t associated_mask;  /* bit j: body j is associated (never tested against) */
+  float accel_x, accel_y;    /* RigidBody.AddAcceleration (Walker.cs:191-198 adds (0, 980)) */
+  float inverse_inertia;     /* < 0: 0.001f * inverse mass (RigidBody.cs:49); >= 0: override (Walker.cs:168) */
+} wb_body_desc;
+typedef struct {
+  int32_t body_a, vertex_a, body_b, vertex_b; /* new Joint(bodyA, bodyB, indexA, indexB), Joint.cs:20-28 */
+} wb_joint_desc;
+/* vertices_xy: all polygons' vertices concatenated in body order, (x, y) interleaved */
+int32_t wb_scene_create(int32_t n_envs, const wb_body_desc* bodies, int32_t n_bodies, const float* vertices_xy, const wb_joint_desc* joints,
+                        int32_t n_joints, int32_t iterations, wb_scene** out);
+int32_t wb_scene_destroy(wb_scene* scene);
+int32_t wb_scene_set_stream(wb_scene* scene, void* cuda_stream);
+/* per-copy record: 2*V vertex floats (body by body), 2B cached centroids, 2B linear velocities, B angular velocities, B tracked
+ * angles, J Joint._currentTorque; host blobs are SoA [floats][N]; collided [N] has one bit per body */
+int32_t wb_scene_state_floats(const wb_scene* scene, int32_t* per_copy_out);
+int32_t wb_scene_set_state(wb_scene* scene, const float* state_host, const int32_t* collided_host);
+int32_t wb_scene_get_state(wb_scene* scene, float* state_host, int32_t* collided_host);
+/* Joint.SetTorque for every joint (Joint.cs:56-61); torques [N][J] */
+int32_t wb_scene_set_torques(wb_scene* scene, const float* torques_host);
+/* Environment.StepObjects(deltaTime) */
+int32_t wb_scene_step_objects(wb_scene* scene, float delta_time);
+
 /* ---- policy: Walker/PPO/PPOAgent.cs, Network/, Matrix.cs ---- */
 /* layer kinds of the network DSL (PPOAgent.ParseLayers, PPOAgent.cs:96-143) */
 enum { WB_DENSE = 0, WB_RELU = 1, WB_LEAKYRELU = 2, WB_TANH = 3 };

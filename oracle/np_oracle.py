@@ -544,3 +544,91 @@ class Environment:
         if self.rigid_bodies[0] is self.floor:
             flags |= 1 << 6
         return np.array(f, np.float32), np.array([flags, self.steps], np.int32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# General scenes: the other IObject shapes and a bare Environment.StepObjects over any body / joint lists
+# (checker for the wb_scene_* path)
+
+def _body_from(material, vectors, is_static=False, is_floor=False, name=""):
+    sk = Skeleton()
+    sk.add_vectors(vectors)
+    return RigidBody(material, sk, is_static=is_static, is_floor=is_floor, name=name)
+
+
+def square_from_size(material, c, size, is_static=False, name="square"):  # Square.cs:18-32
+    adj = f32(f32(0.5) * f32(size))
+    return _body_from(material, [Vec(c.x + adj, c.y + adj), Vec(c.x - adj, c.y + adj), Vec(c.x - adj, c.y - adj), Vec(c.x + adj, c.y - adj)],
+                      is_static, name=name)
+
+
+def triangle_from_size(material, c, size, is_static=False, name="triangle"):  # Triangle.cs:18-31
+    adj = f32(f32(0.5) * f32(size))
+    return _body_from(material, [Vec(c.x, c.y + adj), Vec(c.x - adj, c.y - adj), Vec(c.x + adj, c.y - adj)], is_static, name=name)
+
+
+def hexagon_from_size(material, c, size, is_static=False, name="hexagon"):  # Hexagon.cs:18-34
+    adj = f32(f32(0.5) * f32(size))
+    half = f32(adj * f32(0.5))
+    return _body_from(material, [Vec(c.x + half, c.y + adj), Vec(c.x - half, c.y + adj), Vec(c.x - adj, c.y), Vec(c.x - half, c.y - adj),
+                                 Vec(c.x + half, c.y - adj), Vec(c.x + adj, c.y)], is_static, name=name)
+
+
+def hull_from_positions(material, positions, is_static=False, is_floor=False, name="hull"):  # Hull.cs:18-29
+    return _body_from(material, [Vec(x, y) for x, y in positions], is_static, is_floor, name)
+
+
+def smooth_corners(body, count=1):  # Skeleton.SmoothCorners, Skeleton.cs:33-53 (centroid and box are NOT refreshed)
+    vs = body.skeleton.vectors
+    for _ in range(count):
+        new = []
+        n = len(vs)
+        for j in range(n):
+            face_ab = (vs[(j + 1) % n] - vs[j]) * f32(0.2)
+            face_ac = (vs[cp_mod(j - 1, n)] - vs[j]) * f32(0.2)
+            new.append(vs[j] + face_ac)
+            new.append(vs[j] + face_ab)
+        vs = new
+    body.skeleton.vectors = vs
+    return body
+
+
+class Scene:
+    """Environment.StepObjects (Environment.cs:126-143) over arbitrary lists of bodies and joints."""
+
+    def __init__(self, bodies, joints=(), iterations=50):
+        self.bodies = list(bodies)
+        self.joints = list(joints)
+        self.iterations = iterations
+
+    def set_torques(self, torques):  # Joint.SetTorque for every joint
+        for j, t in zip(self.joints, torques):
+            j.set_torque(t)
+
+    def step_objects(self, dt):
+        dt = f32(f32(dt) / f32(self.iterations))
+        for _ in range(self.iterations):
+            for j in self.joints:
+                j.step()
+            for b in self.bodies:
+                b.trace = None
+                b.step(self.bodies, dt)
+
+    def flat_state(self):
+        """Record of the wb_scene_* path: vertices, centroids, velocities, omega, angle, joint torques; collided bit mask."""
+        f = []
+        for b in self.bodies:
+            for v in b.skeleton.vectors:
+                f += [v.x, v.y]
+        for b in self.bodies:
+            f += [b.skeleton.centroid.x, b.skeleton.centroid.y]
+        for b in self.bodies:
+            f += [b.linear_velocity.x, b.linear_velocity.y]
+        f += [b.angular_velocity for b in self.bodies]
+        f += [b.angle for b in self.bodies]
+        f += [j.current_torque for j in self.joints]
+        collided = 0
+        for i, b in enumerate(self.bodies):
+            if b.collided:
+                collided |= 1 << i
+        return np.array(f, np.float32), collided

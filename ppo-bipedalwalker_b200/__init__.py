@@ -8,4 +8,5 @@ from .env import (DT_FRAME, MATERIALS, Carpet, EnvBatch, Environment, Ice, IMate
 from . import dist  # noqa: F401
 from .ppo import *  # noqa: F401,F403
 from .loop import VectorPPO  # noqa: F401
+from .scene import Hexagon, Hull, IObject, Joint, Pole, Scene, Square, Triangle  # noqa: F401
 from .settings import DeserializeJson, SerializeJson, Settings  # noqa: F401

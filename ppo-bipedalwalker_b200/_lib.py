@@ -34,6 +34,17 @@ class Hyperparams(C.Structure):
                 ("log_std", C.c_float)]
 
 
+class BodyDesc(C.Structure):
+    """wb_body_desc: one IObject of a general scene."""
+    _fields_ = [("n_vertices", C.c_int32), ("is_static", C.c_int32), ("is_floor", C.c_int32), ("material", C.c_int32),
+                ("associated_mask", C.c_uint32), ("accel_x", C.c_float), ("accel_y", C.c_float), ("inverse_inertia", C.c_float)]
+
+
+class JointDesc(C.Structure):
+    """wb_joint_desc: new Joint(bodyA, bodyB, indexA, indexB)."""
+    _fields_ = [("body_a", C.c_int32), ("vertex_a", C.c_int32), ("body_b", C.c_int32), ("vertex_b", C.c_int32)]
+
+
 def declared_symbols() -> list[str]:
     """Every function include/walker_b200.h declares."""
     text = open(HEADER_PATH).read()
@@ -79,6 +90,14 @@ def lib() -> C.CDLL:
         "wb_env_set_variant": (C.c_int32, [vp, C.c_int32]),
         "wb_env_get_variant": (C.c_int32, [vp, ip]),
         "wb_debug_rotz": (C.c_int32, [C.c_int32, vp, C.c_int32, vp, vp]),
+        "wb_scene_create": (C.c_int32, [C.c_int32, C.POINTER(BodyDesc), C.c_int32, vp, C.POINTER(JointDesc), C.c_int32, C.c_int32, C.POINTER(vp)]),
+        "wb_scene_destroy": (C.c_int32, [vp]),
+        "wb_scene_set_stream": (C.c_int32, [vp, vp]),
+        "wb_scene_state_floats": (C.c_int32, [vp, ip]),
+        "wb_scene_set_state": (C.c_int32, [vp, vp, vp]),
+        "wb_scene_get_state": (C.c_int32, [vp, vp, vp]),
+        "wb_scene_set_torques": (C.c_int32, [vp, vp]),
+        "wb_scene_step_objects": (C.c_int32, [vp, C.c_float]),
         "wb_debug_rcp_sqrt_check": (C.c_int32, [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
         "wb_policy_create": (C.c_int32, [C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, hpp, C.POINTER(vp)]),
         "wb_policy_destroy": (C.c_int32, [vp]),

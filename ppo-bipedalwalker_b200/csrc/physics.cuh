@@ -68,4 +68,25 @@ cudaError_t launch_rotz_debug(const float* radians, int n, int mode, float* c_ou
 cudaError_t launch_rcp_sqrt_check(uint32_t first, uint64_t count, unsigned long long* mismatches_dev, uint32_t* first_bad_dev,
                                   cudaStream_t stream);
 
+// ---- general scenes (physics_scene.cu): any list of convex polygons + joints, N lockstep copies
+constexpr int kSceneMaxBodies = 16, kSceneMaxVerts = 16, kSceneMaxJoints = 16;
+struct SceneConst {
+  int32_t n_bodies, n_joints, total_verts, pad;
+  int32_t n_verts[kSceneMaxBodies], vert_offset[kSceneMaxBodies], is_static[kSceneMaxBodies], is_floor[kSceneMaxBodies];
+  uint32_t assoc[kSceneMaxBodies];  // bit j: body j is on this body's "no collide" list (RigidBody.cs:143-152)
+  float inv_mass[kSceneMaxBodies], inv_inertia[kSceneMaxBodies], restitution[kSceneMaxBodies], friction[kSceneMaxBodies];
+  float accel_x[kSceneMaxBodies], accel_y[kSceneMaxBodies];
+  int32_t joint_a[kSceneMaxJoints], joint_ia[kSceneMaxJoints], joint_b[kSceneMaxJoints], joint_ib[kSceneMaxJoints];
+};
+struct SceneParams {
+  float* state;          // [rows][n_pad]: 2*total_verts vertex floats, 2B centroids, 2B velocities, B omega, B angle, J torques
+  int32_t* collided;     // [n_pad] bit per body
+  const float* torques;  // [n][J] or null
+  int32_t n, n_pad;
+  float dt;
+  int32_t iterations;    // 0: no StepObjects (SetTorque only)
+};
+size_t scene_smem_bytes(const SceneConst& s);
+cudaError_t launch_scene(const SceneParams& p, const SceneConst& s, cudaStream_t stream);
+
 }  // namespace wb

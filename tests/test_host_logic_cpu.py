@@ -88,3 +88,21 @@ def test_hyperparameter_json_roundtrip_and_validation(wb, tmp_path):
     assert wb.DeserializeJson(str(path), current=s, log=logged.append) is s and "JSON deserializer error" in logged[-1]
     path.write_text(json.dumps({"Iterations": 50}))
     assert wb.DeserializeJson(str(path), current=s) is s
+
+
+def test_iobject_shape_factories_match_the_numpy_restatement(wb, O):
+    """Square/Triangle/Hexagon/Pole.FromSize and Skeleton.SmoothCorners (Objects/RigidBodies/*.cs, Skeleton.cs:33-53): the host mirror
+    that feeds wb_scene_create and the NumPy restatement produce the same float32 vertex lists."""
+    import np_oracle as P
+    m = (15, 0.3, 1.0)
+    c = (123.4, 567.8)
+    pairs = [(wb.Square.FromSize("Metal", c, 61.7), P.square_from_size(m, P.Vec(*c), 61.7)),
+             (wb.Triangle.FromSize("Metal", c, 33.3), P.triangle_from_size(m, P.Vec(*c), 33.3)),
+             (wb.Hexagon.FromSize("Metal", c, 80.1), P.hexagon_from_size(m, P.Vec(*c), 80.1)),
+             (wb.Pole.FromSize("Metal", c, 75), P.pole_from_size(m, P.Vec(*c), 75, "p")),
+             (wb.Hexagon.FromSize("Metal", c, 80.1).SmoothCorners(1), P.smooth_corners(P.hexagon_from_size(m, P.Vec(*c), 80.1), 1)),
+             (wb.Square.FromSize("Metal", c, 10).SmoothCorners(2), P.smooth_corners(P.square_from_size(m, P.Vec(*c), 10), 2))]
+    for o, b in pairs:
+        ref = np.array([(v.x, v.y) for v in b.skeleton.vectors], np.float32)
+        assert o.vertices.shape == ref.shape and np.array_equal(o.vertices.view(np.uint32), ref.view(np.uint32))
+    assert pairs[-1][0].vertices.shape == (16, 2)  # the largest polygon a scene accepts
