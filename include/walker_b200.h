@@ -246,6 +246,16 @@ int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const flo
                     const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host);
 int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
                         const float* advantages_dev, const float* returns_dev);
+/* Data-parallel variant for one process per GPU on one NVLink/NVSwitch box (no reference equivalent: the reference is one process):
+ * the per-CTA partial gradients are reduced AND summed over all ranks by ONE kernel that pushes slices into the peers' exchange
+ * buffers over NVLink (CUDA IPC peer memory) -- no NCCL call, bit-identical result on every rank.  Setup: every rank calls
+ * wb_comm_local_handle, the 64-byte handles are all-gathered by the host (any transport), every rank calls wb_comm_connect with
+ * the gathered array [world][64].  Every rank must then issue the same sequence of wb_ppo_grad_allreduce_dev calls. */
+int32_t wb_comm_local_handle(wb_policy* p, void* handle64_out);
+int32_t wb_comm_connect(wb_policy* p, int32_t rank, int32_t world, const void* all_handles64);
+int32_t wb_comm_status(wb_policy* p, int32_t* connected_world_out, int32_t* failed_out);
+int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
+                                  const float* advantages_dev, const float* returns_dev);
 /* NeuralNetwork.Optimise -> DenseLayer.Adam on both networks (NeuralNetwork.cs:85-91, DenseLayer.cs:125-159) */
 int32_t wb_adam_step(wb_policy* p);
 /* device address + length of the contiguous gradient buffer [actor | critic | 2 loss sums | skipped] for the

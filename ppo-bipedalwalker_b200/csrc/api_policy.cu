@@ -24,6 +24,13 @@ struct wb_policy {
   // staging for the host-pointer entry points (grown on demand)
   float* d_stage = nullptr;
   size_t stage_floats = 0;
+  // fused reduce + all-reduce over NVLink peer memory (wb_comm_*)
+  float* d_exch = nullptr;       // this rank's exchange buffer (kExchBytes), exported through CUDA IPC
+  uint32_t* d_comm_status = nullptr;
+  ExchPeers peers{};
+  void* opened[kExchMaxWorld] = {};  // IPC mappings to close
+  int comm_rank = -1, comm_world = 0;
+  uint32_t comm_epoch = 0;
 };
 
 static int32_t ensure_stage(wb_policy* p, size_t floats) {
@@ -108,6 +115,10 @@ int32_t wb_policy_destroy(wb_policy* p) {
   cudaFree(p->d_grads);
   cudaFree(p->d_m);
   cudaFree(p->d_v);
+  for (int r = 0; r < kExchMaxWorld; r++)
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
+  cudaFree(p->d_exch);
+  cudaFree(p->d_comm_status);
   cudaFree(p->d_partials);
   cudaFree(p->d_stage);
   delete p;
@@ -343,6 +354,80 @@ int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const 
   const int grid = grid_of(p, n);
   WB_CUDA(run_mlp(p, m));
   WB_CUDA(launch_reduce_partials(p->d_partials, grid, p->d_grads, p->stream));
+  p->launches += 2;
+  return WB_OK;
+}
+
+/* ---- fused gradient reduction + all-reduce over NVLink peer memory ---- */
+int32_t wb_comm_local_handle(wb_policy* p, void* handle64_out) {
+  WB_REQUIRE(p && handle64_out, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!p->d_exch) {
+    WB_CUDA(cudaMalloc(&p->d_exch, kExchBytes));
+    WB_CUDA(cudaMemset(p->d_exch, 0, kExchBytes));
+    WB_CUDA(cudaMalloc(&p->d_comm_status, sizeof(uint32_t)));
+    WB_CUDA(cudaMemset(p->d_comm_status, 0, sizeof(uint32_t)));
+    WB_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  WB_CUDA(cudaIpcGetMemHandle(&h, p->d_exch));
+  memcpy(handle64_out, &h, sizeof(h));
+  return WB_OK;
+}
+
+int32_t wb_comm_connect(wb_policy* p, int32_t rank, int32_t world, const void* all_handles64) {
+  WB_REQUIRE(p && all_handles64, "null argument");
+  WB_REQUIRE(world >= 1 && world <= kExchMaxWorld && rank >= 0 && rank < world, "world must be 1..8 and 0 <= rank < world");
+  WB_REQUIRE(p->d_exch, "call wb_comm_local_handle first");
+  for (int r = 0; r < world; r++) {
+    if (r == rank) {
+      p->peers.base[r] = p->d_exch;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)all_handles64 + (size_t)r * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    WB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->opened[r] = ptr;
+    p->peers.base[r] = (float*)ptr;
+  }
+  p->comm_rank = rank;
+  p->comm_world = world;
+  p->comm_epoch = 0;
+  return WB_OK;
+}
+
+int32_t wb_comm_status(wb_policy* p, int32_t* connected_world_out, int32_t* failed_out) {
+  WB_REQUIRE(p && connected_world_out && failed_out, "null argument");
+  *connected_world_out = p->comm_world;
+  uint32_t st = 0;
+  if (p->d_comm_status) {
+    WB_CUDA(cudaStreamSynchronize(p->stream));
+    WB_CUDA(cudaMemcpy(&st, p->d_comm_status, sizeof(st), cudaMemcpyDeviceToHost));
+  }
+  *failed_out = (int32_t)st;
+  return WB_OK;
+}
+
+int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
+                                  const float* advantages_dev, const float* returns_dev) {
+  WB_REQUIRE(p && states_dev && actions_dev && old_logp_dev && advantages_dev && returns_dev, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  WB_REQUIRE(p->hp.batch_size > 0, "batch_size must be positive");
+  WB_REQUIRE(p->comm_world >= 1, "not connected: call wb_comm_local_handle / wb_comm_connect on every rank first");
+  MlpParams m;
+  fill_mlp_common(p, m, n, kModeGrad);
+  m.states = states_dev;
+  m.actions = actions_dev;
+  m.old_logp = old_logp_dev;
+  m.advantages = advantages_dev;
+  m.returns = returns_dev;
+  m.partials = p->d_partials;
+  const int grid = grid_of(p, n);
+  WB_CUDA(run_mlp(p, m));
+  p->comm_epoch++;
+  WB_CUDA(launch_reduce_exchange(p->d_partials, grid, p->d_grads, p->peers, p->comm_rank, p->comm_world, p->comm_epoch, p->d_comm_status,
+                                 p->stream));
   p->launches += 2;
   return WB_OK;
 }

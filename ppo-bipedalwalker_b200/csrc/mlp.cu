@@ -563,6 +563,86 @@ cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- fused gradient reduction + all-reduce over NVLink peer memory
+// The data-parallel update needs sum over ranks of (sum over this rank's CTAs of the partial gradients): a 24.6 KB message,
+// latency bound.  Instead of reduce_partials_kernel followed by an NCCL all-reduce, ONE kernel does both: CTA c owns float4
+// slice c of the gradient buffer; it sums the rank's per-CTA partials for its slice in fixed order, PUSHES the slice into slot
+// [rank] of every peer's exchange buffer with plain stores over NVLink (peer pointers opened through CUDA IPC), publishes an
+// epoch flag per (peer, rank, slice) with a system-scope release, waits for the world's flags in its OWN buffer (acquire) and
+// adds the world's slots in rank order -- every rank performs the same additions in the same order, so the reduced gradient
+// (and therefore Adam and the weights) is bit-identical everywhere.  Slices are independent (no grid-wide barrier) and the
+// slots are double buffered by epoch parity: a rank can run at most one exchange ahead of the slowest peer.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ grads,
+                                                                       ExchPeers peers, int rank, int world, uint32_t epoch, uint32_t* status) {
+  // 4 threads per float4 of the slice: each sums every 4th per-CTA partial (independent loads in flight), then the four
+  // partial sums are combined pairwise by shuffles -- a fixed order, so the result is deterministic
+  const int part = threadIdx.x & 3;
+  const int i4 = blockIdx.x * (kExchThreads / 4) + (threadIdx.x >> 2);  // float4 index inside the gradient buffer
+  const bool in = i4 < kGradFloats / 4;
+  const int par = (int)(epoch & 1u);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (in) {
+    const float4* p4 = reinterpret_cast<const float4*>(partials) + i4;
+#pragma unroll 4
+    for (int q = part; q < nparts; q += 4) {
+      const float4 v = p4[(size_t)q * (kGradFloats / 4)];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+  }
+#pragma unroll
+  for (int m = 1; m <= 2; m <<= 1) {
+    acc.x += __shfl_xor_sync(0xFFFFFFFFu, acc.x, m);
+    acc.y += __shfl_xor_sync(0xFFFFFFFFu, acc.y, m);
+    acc.z += __shfl_xor_sync(0xFFFFFFFFu, acc.z, m);
+    acc.w += __shfl_xor_sync(0xFFFFFFFFu, acc.w, m);
+  }
+  if (in) {
+    // push my slice into slot [par][rank] of every rank (NVLink stores; r == rank is local); the 4 lanes of an element share the peers
+    for (int r = part; r < world; r += 4) reinterpret_cast<float4*>(peers.base[r] + exch_slot_offset(par, rank))[i4] = acc;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) st_release_sys(exch_flag(peers.base[threadIdx.x], par, rank, blockIdx.x), epoch);
+  if ((int)threadIdx.x < world) {  // wait for rank threadIdx.x's slice in MY buffer
+    const uint32_t* f = exch_flag(peers.base[rank], par, threadIdx.x, blockIdx.x);
+    long spins = 0;
+    while (ld_acquire_sys(f) != epoch) {
+      if (++spins > (1L << 31)) {  // a peer never arrived (crashed?): give up loudly instead of hanging the GPU
+        atomicExch(status, 1u);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (in && part == 0) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; r++) {  // rank order on every rank: bit-identical sums
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(peers.base[rank] + exch_slot_offset(par, r)) + i4);
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+    reinterpret_cast<float4*>(grads)[i4] = s;
+  }
+}
+
+cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
+                                   uint32_t epoch, uint32_t* status, cudaStream_t stream) {
+  reduce_exchange_kernel<<<kExchCtas, kExchThreads, 0, stream>>>(partials, nparts, grads, peers, rank, world, epoch, status);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_reduce_partials(const float* partials, int nparts, float* grads, cudaStream_t stream) {
   reduce_partials_kernel<<<(kGradFloats + 127) / 128, 128, 0, stream>>>(partials, nparts, grads);
   return cudaGetLastError();

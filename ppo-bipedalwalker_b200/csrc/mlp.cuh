@@ -75,6 +75,23 @@ cudaError_t launch_adam(const AdamParams& p, cudaStream_t stream);
 cudaError_t launch_returns(const float* rewards, const float* values, int n, float gamma, float lambda, int use_gae, int normalize,
                            float norm_eps, float* returns, float* advantages, cudaStream_t stream);
 
+// ---- exchange buffer of the fused reduce + all-reduce (one allocation per rank, shared with the peers through CUDA IPC)
+constexpr int kExchMaxWorld = 8;
+constexpr int kExchThreads = 512;
+constexpr int kExchCtas = (kGradFloats / 4 + kExchThreads / 4 - 1) / (kExchThreads / 4);  // 13 slices of 128 float4 (4 threads per float4)
+struct ExchPeers {
+  float* base[kExchMaxWorld];  // every rank's exchange buffer as seen from this process
+};
+// layout (floats): slots [2 parities][kExchMaxWorld ranks][kGradFloats], then flags (uint32) [2][kExchMaxWorld][kExchCtas]
+constexpr size_t kExchSlotFloats = (size_t)2 * kExchMaxWorld * kGradFloats;
+constexpr size_t kExchBytes = kExchSlotFloats * sizeof(float) + (size_t)2 * kExchMaxWorld * kExchCtas * sizeof(uint32_t);
+__host__ __device__ inline size_t exch_slot_offset(int parity, int rank) { return ((size_t)parity * kExchMaxWorld + rank) * kGradFloats; }
+__host__ __device__ inline uint32_t* exch_flag(float* base, int parity, int rank, int cta) {
+  return reinterpret_cast<uint32_t*>(base + kExchSlotFloats) + ((size_t)parity * kExchMaxWorld + rank) * kExchCtas + cta;
+}
+cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
+                                   uint32_t epoch, uint32_t* status, cudaStream_t stream);
+
 cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, int n_envs, int T, float gamma,
                                    float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream);
 cudaError_t launch_gather_minibatch(const int32_t* index, int B, const float* states, const float* actions, const float* logp,

@@ -40,6 +40,31 @@ def allreduce_sum_(tensor):
     return tensor
 
 
+def connect_peers(agent) -> bool:
+    """Wire `agent` (one per rank) for the fused gradient reduction + all-reduce over NVLink peer memory: every rank exports its
+    exchange buffer as a CUDA IPC handle, the 64-byte handles are all-gathered through the existing process group, every rank
+    maps its peers' buffers.  Returns False (NCCL path stays in use) without an initialised multi-rank group."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from ._lib import check, lib
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2 or dist.get_world_size() > 8:
+        return False
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_ubyte * 64)()
+    check(lib().wb_comm_local_handle(agent._h, buf))
+    cuda = dist.get_backend() == "nccl"
+    mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda" if cuda else "cpu")
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    handles = bytes(torch.cat(gathered).cpu().numpy().tobytes())
+    check(lib().wb_comm_connect(agent._h, rank, world, handles))
+    dist.barrier()  # nobody pushes before everybody has mapped everybody
+    return True
+
+
 def train_minibatch_sharded(agent, states, actions, logp, advantages, returns, grad_view=None):
     """One data-parallel PPO minibatch: local gradient over this rank's shard (already divided by the GLOBAL
     batch size hp.batch_size), all-reduce(sum), identical Adam on every rank (weights stay bit-identical)."""

@@ -31,7 +31,8 @@ from .ppo import PPOAgent
 
 class VectorPPO:
     def __init__(self, n_envs_global: int, horizon: int = 64, minibatch_global: int = 65536, epochs: int = 1,
-                 floor="Metal", walker="Carpet", hp: Hyperparams | None = None, seed: int = 0, policy_variant: int | None = None):
+                 floor="Metal", walker="Carpet", hp: Hyperparams | None = None, seed: int = 0, policy_variant: int | None = None,
+                 fused_allreduce: bool = True):
         import torch
         self.torch = torch
         self.rank, self.local_rank, self.world = _dist.world()
@@ -69,6 +70,9 @@ class VectorPPO:
         self.mb = [torch.empty(self.mb_local, OBS, **f32), torch.empty(self.mb_local, ACT, **f32), torch.empty(self.mb_local, ACT, **f32),
                    torch.empty(self.mb_local, **f32), torch.empty(self.mb_local, **f32)]
         self.grad_view = _dist.grad_tensor(self.agent)
+        # multi-GPU: the gradient all-reduce is fused into the reduction kernel (NVLink peer memory, dist.connect_peers);
+        # fused_allreduce=False keeps the NCCL all-reduce (same result, one more launch + the NCCL latency per mini-batch)
+        self.fused = bool(fused_allreduce) and _dist.connect_peers(self.agent)
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed * 1000003 + self.rank)
         self.step_counter = 0
@@ -103,8 +107,11 @@ class VectorPPO:
             for j in range(n_mb):
                 idx = perm[j * self.mb_local:(j + 1) * self.mb_local]
                 check(L.wb_gather_minibatch_dev(h, self.mb_local, ptr(idx), ptr(S), ptr(A), ptr(LP), ptr(ADV), ptr(RET), *[ptr(m) for m in self.mb]))
-                check(L.wb_ppo_grad_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
-                _dist.allreduce_sum_(self.grad_view)
+                if self.fused:
+                    check(L.wb_ppo_grad_allreduce_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
+                else:
+                    check(L.wb_ppo_grad_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
+                    _dist.allreduce_sum_(self.grad_view)
                 check(L.wb_adam_step(h))
         losses = self.grad_view[-3:].clone()  # [sum g_V, sum mean_k g_mu, skipped] of the last mini-batch (PPOAgent.cs:331-332)
         return n_mb * self.epochs, losses
