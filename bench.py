@@ -187,8 +187,7 @@ def bench_ppo(wb, torch, stream, steps, warmup, flush):
     L = lib()
 
     def one():
-        check(L.wb_ppo_grad_dev(agent._h, n, *[ptr(t) for t in dev]))
-        check(L.wb_adam_step(agent._h))
+        check(L.wb_ppo_train_dev(agent._h, n, *[ptr(t) for t in dev]))  # gradient kernel + fused reduce / Adam kernel
 
     for _ in range(warmup):
         one()

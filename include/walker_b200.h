@@ -256,6 +256,11 @@ int32_t wb_comm_connect(wb_policy* p, int32_t rank, int32_t world, const void* a
 int32_t wb_comm_status(wb_policy* p, int32_t* connected_world_out, int32_t* failed_out);
 int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
                                   const float* advantages_dev, const float* returns_dev);
+/* PPOAgent.Train(Batch) complete (PPOAgent.cs:218-345) in TWO launches: the gradient kernel, then ONE kernel that reduces the per-CTA
+ * partials, all-reduces them over NVLink when the policy is connected (wb_comm_connect; a single rank otherwise) and applies
+ * DenseLayer.Adam to both networks -- the reduced gradient is also left in the gradient buffer (losses / skipped included) */
+int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
+                         const float* advantages_dev, const float* returns_dev);
 /* NeuralNetwork.Optimise -> DenseLayer.Adam on both networks (NeuralNetwork.cs:85-91, DenseLayer.cs:125-159) */
 int32_t wb_adam_step(wb_policy* p);
 /* device address + length of the contiguous gradient buffer [actor | critic | 2 loss sums | skipped] for the

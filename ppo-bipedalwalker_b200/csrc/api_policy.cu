@@ -427,7 +427,53 @@ int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_d
   WB_CUDA(run_mlp(p, m));
   p->comm_epoch++;
   WB_CUDA(launch_reduce_exchange(p->d_partials, grid, p->d_grads, p->peers, p->comm_rank, p->comm_world, p->comm_epoch, p->d_comm_status,
-                                 p->stream));
+                                 nullptr, p->stream));
+  p->launches += 2;
+  return WB_OK;
+}
+
+static void next_adam_params(wb_policy* p, AdamParams& a) {
+  a = AdamParams{};
+  a.params = p->d_params;
+  a.grads = p->d_grads;
+  a.m = p->d_m;
+  a.v = p->d_v;
+  a.alpha = p->hp.alpha;
+  a.beta1 = p->hp.beta1;
+  a.beta2 = p->hp.beta2;
+  a.eps = p->hp.adam_epsilon;
+  for (int l = 0; l < 5; l++) {
+    p->iterations[l] += 1;  // DenseLayer.cs:127
+    a.corr1[l] = (float)(1.0 - pow((double)p->hp.beta1, (double)p->iterations[l]));  // :142-145
+    a.corr2[l] = (float)(1.0 - pow((double)p->hp.beta2, (double)p->iterations[l]));
+  }
+}
+
+int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
+                         const float* advantages_dev, const float* returns_dev) {
+  WB_REQUIRE(p && states_dev && actions_dev && old_logp_dev && advantages_dev && returns_dev, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  WB_REQUIRE(p->hp.batch_size > 0, "batch_size must be positive");
+  if (!p->d_comm_status) {
+    WB_CUDA(cudaMalloc(&p->d_comm_status, sizeof(uint32_t)));
+    WB_CUDA(cudaMemset(p->d_comm_status, 0, sizeof(uint32_t)));
+  }
+  MlpParams m;
+  fill_mlp_common(p, m, n, kModeGrad);
+  m.states = states_dev;
+  m.actions = actions_dev;
+  m.old_logp = old_logp_dev;
+  m.advantages = advantages_dev;
+  m.returns = returns_dev;
+  m.partials = p->d_partials;
+  const int grid = grid_of(p, n);
+  WB_CUDA(run_mlp(p, m));
+  AdamParams a;
+  next_adam_params(p, a);
+  const int world = p->comm_world >= 2 ? p->comm_world : 1;
+  if (world > 1) p->comm_epoch++;
+  WB_CUDA(launch_reduce_exchange(p->d_partials, grid, p->d_grads, p->peers, world > 1 ? p->comm_rank : 0, world, p->comm_epoch,
+                                 p->d_comm_status, &a, p->stream));
   p->launches += 2;
   return WB_OK;
 }
@@ -462,20 +508,8 @@ int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const flo
 
 int32_t wb_adam_step(wb_policy* p) {
   WB_REQUIRE(p, "policy is null");
-  AdamParams a{};
-  a.params = p->d_params;
-  a.grads = p->d_grads;
-  a.m = p->d_m;
-  a.v = p->d_v;
-  a.alpha = p->hp.alpha;
-  a.beta1 = p->hp.beta1;
-  a.beta2 = p->hp.beta2;
-  a.eps = p->hp.adam_epsilon;
-  for (int l = 0; l < 5; l++) {
-    p->iterations[l] += 1;  // DenseLayer.cs:127
-    a.corr1[l] = (float)(1.0 - pow((double)p->hp.beta1, (double)p->iterations[l]));  // :142-145
-    a.corr2[l] = (float)(1.0 - pow((double)p->hp.beta2, (double)p->iterations[l]));
-  }
+  AdamParams a;
+  next_adam_params(p, a);
   WB_CUDA(launch_adam(a, p->stream));
   p->launches++;
   return WB_OK;

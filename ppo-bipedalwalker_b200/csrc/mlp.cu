@@ -413,12 +413,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
   grads[i] = sum;
 }
 
-// DenseLayer.Adam, DenseLayer.cs:125-159 (every product and sum individually rounded, as the Matrix operators do)
-__global__ void adam_kernel(const AdamParams a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kTotalParams) return;
+// DenseLayer.Adam for one parameter (DenseLayer.cs:125-159; every product and sum individually rounded, as the Matrix operators do)
+__device__ __forceinline__ void adam_update(const AdamParams& a, int i, float g) {
   const int layer = (i < kOffW2) ? 0 : (i < kOffW3) ? 1 : (i < kActorParams) ? 2 : (i < kOffWc2) ? 3 : 4;
-  const float g = a.grads[i];
   const float m = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, a.beta1), g), __fmul_rn(a.beta1, a.m[i]));
   const float v = __fadd_rn(__fmul_rn(a.beta2, a.v[i]), __fmul_rn(__fsub_rn(1.0f, a.beta2), __fmul_rn(g, g)));
   a.m[i] = m;
@@ -427,6 +424,12 @@ __global__ void adam_kernel(const AdamParams a) {
   const float vhat = __fdiv_rn(v, a.corr2[layer]);
   const float denom = __fadd_rn(__fsqrt_rn(vhat), a.eps);
   a.params[i] = __fsub_rn(a.params[i], __fmul_rn(a.alpha, __fdiv_rn(mhat, denom)));
+}
+
+__global__ void adam_kernel(const AdamParams a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kTotalParams) return;
+  adam_update(a, i, a.grads[i]);
 }
 
 // PPOAgent.MonteCarloReturn/MonteCarloAdvantages (:475-498), GeneralizedAdvantageEstimate (:414-444, whose nextGae is
@@ -580,7 +583,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 
 __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ grads,
-                                                                       ExchPeers peers, int rank, int world, uint32_t epoch, uint32_t* status) {
+                                                                       ExchPeers peers, int rank, int world, uint32_t epoch, uint32_t* status,
+                                                                       AdamParams adam, int do_adam) {
   // 4 threads per float4 of the slice: each sums every 4th per-CTA partial (independent loads in flight), then the four
   // partial sums are combined pairwise by shuffles -- a fixed order, so the result is deterministic
   const int part = threadIdx.x & 3;
@@ -606,40 +610,53 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
     acc.z += __shfl_xor_sync(0xFFFFFFFFu, acc.z, m);
     acc.w += __shfl_xor_sync(0xFFFFFFFFu, acc.w, m);
   }
-  if (in) {
-    // push my slice into slot [par][rank] of every rank (NVLink stores; r == rank is local); the 4 lanes of an element share the peers
-    for (int r = part; r < world; r += 4) reinterpret_cast<float4*>(peers.base[r] + exch_slot_offset(par, rank))[i4] = acc;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < world) st_release_sys(exch_flag(peers.base[threadIdx.x], par, rank, blockIdx.x), epoch);
-  if ((int)threadIdx.x < world) {  // wait for rank threadIdx.x's slice in MY buffer
-    const uint32_t* f = exch_flag(peers.base[rank], par, threadIdx.x, blockIdx.x);
-    long spins = 0;
-    while (ld_acquire_sys(f) != epoch) {
-      if (++spins > (1L << 31)) {  // a peer never arrived (crashed?): give up loudly instead of hanging the GPU
-        atomicExch(status, 1u);
-        break;
+  float4 s = acc;
+  if (world > 1) {  // (world is a kernel argument: uniform)
+    if (in) {
+      // push my slice into slot [par][rank] of every rank (NVLink stores; r == rank is local); the 4 lanes of an element share the peers
+      for (int r = part; r < world; r += 4) reinterpret_cast<float4*>(peers.base[r] + exch_slot_offset(par, rank))[i4] = acc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) st_release_sys(exch_flag(peers.base[threadIdx.x], par, rank, blockIdx.x), epoch);
+    if ((int)threadIdx.x < world) {  // wait for rank threadIdx.x's slice in MY buffer
+      const uint32_t* f = exch_flag(peers.base[rank], par, threadIdx.x, blockIdx.x);
+      long spins = 0;
+      while (ld_acquire_sys(f) != epoch) {
+        if (++spins > (1L << 31)) {  // a peer never arrived (crashed?): give up loudly instead of hanging the GPU
+          atomicExch(status, 1u);
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (in && part == 0) {
+      s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < world; r++) {  // rank order on every rank: bit-identical sums
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(peers.base[rank] + exch_slot_offset(par, r)) + i4);
+        s.x += v.x;
+        s.y += v.y;
+        s.z += v.z;
+        s.w += v.w;
       }
     }
   }
-  __syncthreads();
   if (in && part == 0) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; r++) {  // rank order on every rank: bit-identical sums
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(peers.base[rank] + exch_slot_offset(par, r)) + i4);
-      s.x += v.x;
-      s.y += v.y;
-      s.z += v.z;
-      s.w += v.w;
-    }
     reinterpret_cast<float4*>(grads)[i4] = s;
+    if (do_adam) {  // NeuralNetwork.Optimise fused behind the reduction: the gradient never makes another round trip
+      const float g[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        if (i4 * 4 + c < kTotalParams) adam_update(adam, i4 * 4 + c, g[c]);
+    }
   }
 }
 
 cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
-                                   uint32_t epoch, uint32_t* status, cudaStream_t stream) {
-  reduce_exchange_kernel<<<kExchCtas, kExchThreads, 0, stream>>>(partials, nparts, grads, peers, rank, world, epoch, status);
+                                   uint32_t epoch, uint32_t* status, const AdamParams* adam, cudaStream_t stream) {
+  AdamParams a{};
+  if (adam) a = *adam;
+  reduce_exchange_kernel<<<kExchCtas, kExchThreads, 0, stream>>>(partials, nparts, grads, peers, rank, world, epoch, status, a, adam != nullptr);
   return cudaGetLastError();
 }
 

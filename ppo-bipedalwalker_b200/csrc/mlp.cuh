@@ -89,8 +89,9 @@ __host__ __device__ inline size_t exch_slot_offset(int parity, int rank) { retur
 __host__ __device__ inline uint32_t* exch_flag(float* base, int parity, int rank, int cta) {
   return reinterpret_cast<uint32_t*>(base + kExchSlotFloats) + ((size_t)parity * kExchMaxWorld + rank) * kExchCtas + cta;
 }
+// adam != nullptr: DenseLayer.Adam is applied to the reduced gradient inside the same kernel
 cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
-                                   uint32_t epoch, uint32_t* status, cudaStream_t stream);
+                                   uint32_t epoch, uint32_t* status, const AdamParams* adam, cudaStream_t stream);
 
 cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, int n_envs, int T, float gamma,
                                    float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream);

@@ -9,12 +9,13 @@ values, returns, advantages, Epochs x shuffled mini-batches of Train(Batch) -- r
             actions and their log-probabilities -- Environment.cs:87-88 --, rewards, dones, values) stays in HBM, time-major.
   update    wb_segment_returns_dev (MC return / the reference's GAE per episode fragment), then `epochs` x (pool / minibatch)
             mini-batches: index permutation (sampling without replacement, remainder dropped, PPOAgent.cs:501-540) ->
-            wb_gather_minibatch_dev -> wb_ppo_grad_dev -> all-reduce(sum) of the 6 152-float gradient buffer -> wb_adam_step.
+            wb_gather_minibatch_dev -> wb_ppo_train_dev (gradient kernel + ONE kernel that reduces the partial gradients,
+            all-reduces the 6 152-float buffer over NVLink peer memory and applies Adam; NCCL all-reduce as the fallback).
 
 Multi-GPU (one process per GPU, torchrun): the walkers are block-sharded, rollouts never communicate; every rank draws its
 share (minibatch / world) of each global mini-batch from its OWN pool, gradients are divided by the GLOBAL batch size inside
-the kernel, so one NCCL all-reduce(sum) per mini-batch makes every rank apply the identical Adam step (weights stay
-bit-identical across ranks).  PyTorch is used for device buffers, the permutation and the collective only.
+the kernel, so one all-reduce(sum) per mini-batch makes every rank apply the identical Adam step (weights stay bit-identical
+across ranks).  PyTorch is used for device buffers, the permutation and process-group plumbing only.
 """
 from __future__ import annotations
 
@@ -107,12 +108,13 @@ class VectorPPO:
             for j in range(n_mb):
                 idx = perm[j * self.mb_local:(j + 1) * self.mb_local]
                 check(L.wb_gather_minibatch_dev(h, self.mb_local, ptr(idx), ptr(S), ptr(A), ptr(LP), ptr(ADV), ptr(RET), *[ptr(m) for m in self.mb]))
-                if self.fused:
-                    check(L.wb_ppo_grad_allreduce_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
+                if self.fused or self.world == 1:
+                    # gradient kernel, then ONE kernel: reduce partials (+ all-reduce over NVLink peer memory) + Adam
+                    check(L.wb_ppo_train_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
                 else:
                     check(L.wb_ppo_grad_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
                     _dist.allreduce_sum_(self.grad_view)
-                check(L.wb_adam_step(h))
+                    check(L.wb_adam_step(h))
         losses = self.grad_view[-3:].clone()  # [sum g_V, sum mean_k g_mu, skipped] of the last mini-batch (PPOAgent.cs:331-332)
         return n_mb * self.epochs, losses
 

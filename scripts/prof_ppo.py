@@ -17,7 +17,7 @@ for variant in variants:
            (-0.5 * rng.random((n, 4))).astype(np.float32), rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32))]
     L = lib()
     def one():
-        check(L.wb_ppo_grad_dev(agent._h, n, *[ptr(t) for t in dev])); check(L.wb_adam_step(agent._h))
+        check(L.wb_ppo_train_dev(agent._h, n, *[ptr(t) for t in dev]))
     for _ in range(3): one()
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

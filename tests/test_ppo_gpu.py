@@ -252,3 +252,28 @@ def test_tensor_core_and_cuda_core_kernels_agree(gpu, O):
     m1, v1 = a1.FeedForward(states[:5000])
     np.testing.assert_allclose(m0, m1, rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(v0, v1, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_fused_train_step_tracks_oracle(gpu, O, variant):
+    """wb_ppo_train_dev: gradient kernel + ONE kernel that reduces the per-CTA partials and applies DenseLayer.Adam; five
+    consecutive minibatches against the oracle's per-sample update, and against the unfused wb_ppo_grad_dev + wb_adam_step."""
+    import torch
+    from ppo_bipedalwalker_b200._lib import check, lib, ptr
+    agent, actor, critic, ohp = make_pair(gpu, O, 21, batch_size=512, variant=variant)
+    twin, _, _, _ = make_pair(gpu, O, 21, batch_size=512, variant=variant)
+    rng = np.random.default_rng(21)
+    for it in range(5):
+        batch = synth_batch(rng, actor, 512, critic_flat=critic.get_params())
+        dev = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in batch]
+        check(lib().wb_ppo_train_dev(agent._h, 512, *[ptr(t) for t in dev]))
+        check(lib().wb_ppo_grad_dev(twin._h, 512, *[ptr(t) for t in dev]))
+        check(lib().wb_adam_step(twin._h))
+        O.ppo_train_batch(actor, critic, ohp, *batch, optimise=True)
+        agent.sync()
+        np.testing.assert_allclose(agent.actor.get_flat(), actor.get_params(), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(agent.critic.get_flat(), critic.get_params(), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(agent.actor.get_flat(), twin.actor.get_flat(), rtol=0, atol=2e-6)
+        assert rel_err(agent.actor.get_grads(), twin.actor.get_grads()) < 1e-6
+    m, v, its = agent.actor.get_adam()
+    assert list(its) == [5, 5, 5]
