@@ -407,6 +407,13 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
     bool sep = false;
     // Projection.IsOverlapping + depth (SATCollision.cs:47-50,100-104): symmetric in the two projections.  Returns true when
     // no env of the warp needs another axis.
+    // kVote: normally the rounds stop as soon as no walker of the warp needs another axis (one vote per round).  With G == 4
+    // (the 8-lanes-per-walker layout of the 4096-walker case: latency bound, 8 pairs in flight per warp, so an early stop is
+    // rare) the three rounds are fully unrolled WITHOUT votes: a straight-line block lets the rounds' long dependency chains
+    // (edge -> 1/sqrt -> 12 dot products -> min/max tree) overlap; the separation flags meet in one vote after the last round.
+    // Measured at 4096 walkers: G = 4 0.472 -> 0.452 ms per env-step; G = 8 (throughput bound) 0.474 -> 0.596, so it keeps the votes.
+    constexpr bool kVote = G != 4;
+    bool my_sep = false;
     auto accumulate = [&](bool use, float2 axis, int axis_idx, float omin, float omax, float tmin, float tmax) {
       const float temp = fminf(fsub(tmax, omin), fsub(omax, tmin));
       const bool overlapping = (omin < tmax) && (tmin < omax);
@@ -415,7 +422,11 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
         normal = axis;
         idx = axis_idx;
       }
-      if (sep_axis != nullptr && use && !overlapping && !sep) *sep_axis = axis_idx;
+      if (sep_axis != nullptr && use && !overlapping && !sep && !my_sep) *sep_axis = axis_idx;
+      if (!kVote) {
+        my_sep = my_sep || (use && !overlapping);
+        return false;
+      }
       const bool separated = group_any<EV, G>(e, use && !overlapping);  // (a vote: every lane takes part, no short-circuit)
       sep = sep || separated;
       return !__any_sync(kFull, hit && !sep);
@@ -428,43 +439,60 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
       skip = (axis.x == 0.0f) && (axis.y == 0.0f);
       return vnormalize_fast(axis);
     };
-    if (FLOORB) {
-      bool done = false;
+    auto round_a_vs_floor = [&](int r) {  // AxisChecks(A, floor): A's 6 edges
+      const int i = r + e.gsub;
+      const bool valid = i < 6;
+      bool skip;
+      const float2 axis = edge_axis(A, valid ? i : 0, skip);
+      float omin, omax, tmin, tmax;
+      project6(PA, axis, omin, omax);
+      project4(fl.v, axis, tmin, tmax);
+      return accumulate(valid && !skip, axis, i, omin, omax, tmin, tmax);
+    };
+    auto round_floor_vs_a = [&](int r) {  // AxisChecks(floor, A): constant axes and constant own projection
+      const int i = r + e.gsub;
+      const bool valid = i < 4;
+      const int k = valid ? i : 0;
+      const float2 axis = fl.axis[k];
+      float tmin, tmax;
+      project6(PA, axis, tmin, tmax);
+      return accumulate(valid && fl.skip[k] == 0, axis, nA + k, fl.pmin[k], fl.pmax[k], tmin, tmax);
+    };
+    auto round_pole = [&](int r) {  // AxisChecks(A, B) then AxisChecks(B, A)
+      const int i = r + e.gsub;
+      const bool valid = i < 12;
+      const bool ownA = i < 6;
+      const int k = ownA ? i : (valid ? i - 6 : 0);
+      bool skip;
+      const float2 axis = edge_axis(ownA ? A : B, k, skip);
+      float amn, amx, bmn, bmx;
+      project6(PA, axis, amn, amx);
+      project6(PB, axis, bmn, bmx);
+      return accumulate(valid && !skip, axis, ownA ? i : nA + k, amn, amx, bmn, bmx);
+    };
+    if (kVote) {
+      if (FLOORB) {
+        bool done = false;
 #pragma unroll 1
-      for (int r = 0; r < 6 && !done; r += G) {  // AxisChecks(A, floor): A's 6 edges
-        const int i = r + e.gsub;
-        const bool valid = i < 6;
-        bool skip;
-        const float2 axis = edge_axis(A, valid ? i : 0, skip);
-        float omin, omax, tmin, tmax;
-        project6(PA, axis, omin, omax);
-        project4(fl.v, axis, tmin, tmax);
-        done = accumulate(valid && !skip, axis, i, omin, omax, tmin, tmax);
-      }
+        for (int r = 0; r < 6 && !done; r += G) done = round_a_vs_floor(r);
 #pragma unroll 1
-      for (int r = 0; r < 4 && !done; r += G) {  // AxisChecks(floor, A): constant axes and constant own projection
-        const int i = r + e.gsub;
-        const bool valid = i < 4;
-        const int k = valid ? i : 0;
-        const float2 axis = fl.axis[k];
-        float tmin, tmax;
-        project6(PA, axis, tmin, tmax);
-        done = accumulate(valid && fl.skip[k] == 0, axis, nA + k, fl.pmin[k], fl.pmax[k], tmin, tmax);
+        for (int r = 0; r < 4 && !done; r += G) done = round_floor_vs_a(r);
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < 12; r += G)
+          if (round_pole(r)) break;
       }
     } else {
-#pragma unroll 1
-      for (int r = 0; r < 12; r += G) {  // AxisChecks(A, B) then AxisChecks(B, A)
-        const int i = r + e.gsub;
-        const bool valid = i < 12;
-        const bool ownA = i < 6;
-        const int k = ownA ? i : (valid ? i - 6 : 0);
-        bool skip;
-        const float2 axis = edge_axis(ownA ? A : B, k, skip);
-        float amn, amx, bmn, bmx;
-        project6(PA, axis, amn, amx);
-        project6(PB, axis, bmn, bmx);
-        if (accumulate(valid && !skip, axis, ownA ? i : nA + k, amn, amx, bmn, bmx)) break;
+      if (FLOORB) {
+#pragma unroll
+        for (int r = 0; r < 6; r += G) round_a_vs_floor(r);
+#pragma unroll
+        for (int r = 0; r < 4; r += G) round_floor_vs_a(r);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 12; r += G) round_pole(r);
       }
+      sep = group_any<EV, G>(e, my_sep);
     }
     colliding = hit && !sep;
     if (__any_sync(kFull, colliding)) {
@@ -614,7 +642,7 @@ __device__ __forceinline__ int record_word(int f) {
 }
 
 template <int L, int LEGS, bool TRACE>
-__global__ void __launch_bounds__(32, 16) physics_lanes_kernel(const PhysicsParams p) {
+__global__ void __launch_bounds__(32, (L <= 2) ? 16 : 8) physics_lanes_kernel(const PhysicsParams p) {
   static_assert(LEGS == 1 || (LEGS == 2 && L >= 2), "the leg split needs at least two lanes per environment");
   constexpr int E = 32 / L;
   __shared__ __align__(16) float s_state[(kV2Count * 2 + kFCount) * E];
