@@ -374,7 +374,7 @@ int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out) {
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env) {
   WB_REQUIRE(env, "env is null");
   if (lanes_per_env == 0) lanes_per_env = default_lanes(env->n, env->sm_count);
-  if (!physics_lanes_supported(lanes_per_env)) return fail(WB_ERR_INVALID, "variant must be 1, 2, 4, 8 or 16 lanes per walker, 104 / 108 / 116 (no leg split) or 1001 / 1002 / 1003 (compacting throughput kernels)");
+  if (!physics_lanes_supported(lanes_per_env)) return fail(WB_ERR_INVALID, "variant must be 1, 2, 4, 8 or 16 lanes per walker, 104 / 108 / 116 (no leg split) 1001 / 1002 / 1003 or 1011-1015 (compacting throughput kernels)");
   env->lanes = lanes_per_env;
   return WB_OK;
 }

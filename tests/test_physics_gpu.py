@@ -126,7 +126,7 @@ def test_user_material_plugin(gpu, O):
     assert_state_equal(env, ref, "custom material")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 4, 1001, 1002])
+@pytest.mark.parametrize("variant", [0, 1, 4, 1001, 1002, 1011, 1012])
 def test_ragged_batch_sizes(gpu, O, variant):
     """Batch sizes that leave partially filled warps / CTAs / SoA padding, for the auto-selected kernel and explicit variants."""
     for n in (1, 7, 9, 33, 300):
@@ -228,7 +228,7 @@ def test_rotation_coefficients_match_libm_rounded_to_float(gpu, O, mode):
         assert bad_c == 0 and bad_s == 0
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32, 104, 108, 116, 1001, 1002, 1003])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32, 104, 108, 116, 1001, 1002, 1003, 1004, 1011, 1012, 1013, 1014, 1015, 1016])
 def test_kernel_variants_bit_exact(gpu, O, lanes):
     """Both thread mappings (two envs per warp / one env per warp) against the oracle, traces included."""
     n = 40
