@@ -7,7 +7,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwalker_b200.so")
+LIB_PATH = os.environ.get("WB_LIB_PATH") or os.path.join(_HERE, "lib", "libwalker_b200.so")  # WB_LIB_PATH: A/B builds of the same library
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "walker_b200.h")
 
 WB_OK = 0

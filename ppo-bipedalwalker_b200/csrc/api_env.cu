@@ -153,9 +153,9 @@ using namespace wb;
 // a walker split its SAT axes and vertices; with many, one lane per walker does no redundant work (see physics_lanes.cu).
 static int default_lanes(int n_envs, int sm_count) {
   const long per_sm = ((long)n_envs + sm_count - 1) / sm_count;
-  if (per_sm <= 64) return 8;
+  if (per_sm <= 40) return 8;
   if (per_sm <= 160) return 4;
-  if (per_sm <= 320) return 2;
+  if (per_sm <= 200) return 2;
   return 1001;  // GPU full: one thread per walker with CTA-level work compaction
 }
 
@@ -374,7 +374,7 @@ int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out) {
 int32_t wb_env_set_variant(wb_env_batch* env, int32_t lanes_per_env) {
   WB_REQUIRE(env, "env is null");
   if (lanes_per_env == 0) lanes_per_env = default_lanes(env->n, env->sm_count);
-  if (!physics_lanes_supported(lanes_per_env)) return fail(WB_ERR_INVALID, "variant must be 1, 2, 4, 8 or 16 lanes per walker, 104 / 108 / 116 (no leg split) 1001 / 1002 / 1003 or 1011-1015 (compacting throughput kernels)");
+  if (!physics_lanes_supported(lanes_per_env)) return fail(WB_ERR_INVALID, "variant must be 1, 2, 4, 8 or 16 lanes per walker, 104 / 108 / 116 (no leg split) or 1001 / 1002 / 1003 (compacting throughput kernels)");
   env->lanes = lanes_per_env;
   return WB_OK;
 }
@@ -484,6 +484,17 @@ int32_t wb_env_get_obs(wb_env_batch* env, float* obs_host) {
   return copy_out(env, obs_host, nullptr, nullptr);
 }
 
+// Pinned (page-locked) host memory is addressable from the device under unified addressing: the device-side alias of `p`, or
+// null when `p` is ordinary pageable memory
+static void* device_alias_of_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
+
 static int step_phases(int32_t auto_reset) {
   return kPhaseIncSteps | kPhaseTakeActions | kPhaseStepObjects | kPhaseObserve | (auto_reset ? kPhaseAutoReset : 0);
 }
@@ -491,6 +502,22 @@ static int step_phases(int32_t auto_reset) {
 int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_time, int32_t auto_reset, float* obs_host,
                     float* reward_host, uint8_t* done_host) {
   WB_REQUIRE(env && actions_host, "null argument");
+  // Zero-copy path: when every host buffer of the call is pinned, the kernel reads the actions and writes the observations,
+  // rewards and done flags straight through the device-side aliases of the caller's buffers (16 B / 53 B per walker over
+  // PCIe, issued by the kernel itself) -- no staging copies, one launch and one synchronisation per env-step.  Pageable
+  // buffers (or WB_NO_ZERO_COPY=1) take the staged path: H2D copy, launch, three D2H copies.
+  static const bool zero_copy_enabled = getenv("WB_NO_ZERO_COPY") == nullptr;
+  if (zero_copy_enabled) {
+    const float* a = static_cast<const float*>(device_alias_of_pinned(actions_host));
+    float* o = obs_host ? static_cast<float*>(device_alias_of_pinned(obs_host)) : env->d_obs;
+    float* r = reward_host ? static_cast<float*>(device_alias_of_pinned(reward_host)) : env->d_reward;
+    uint8_t* d = done_host ? static_cast<uint8_t*>(device_alias_of_pinned(done_host)) : env->d_done;
+    if (a && o && r && d && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+      if (int32_t rc = launch(env, step_phases(auto_reset), delta_time, a, o, r, d, nullptr, nullptr, nullptr)) return rc;
+      WB_CUDA(cudaStreamSynchronize(env->stream));
+      return WB_OK;
+    }
+  }
   WB_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, sizeof(float) * WB_ACT * env->n, cudaMemcpyHostToDevice, env->stream));
   if (int32_t rc = launch(env, step_phases(auto_reset), delta_time, env->d_actions, env->d_obs, env->d_reward, env->d_done, nullptr,
                           nullptr, nullptr))

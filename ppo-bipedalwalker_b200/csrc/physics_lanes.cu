@@ -1135,7 +1135,7 @@ __device__ __noinline__ void drain(Shared<kE>& S, int parity) {
 }
 
 template <int kE>
-__global__ void __launch_bounds__(kE, kE == 192 ? 3 : 512 / kE) physics_compact_kernel(const PhysicsParams p) {
+__global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const PhysicsParams p) {
   using EV = Env<1, kE>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared<kE>& S = *reinterpret_cast<Shared<kE>*>(smem_raw);
@@ -1331,364 +1331,6 @@ static cudaError_t launch_compact(const PhysicsParams& p, cudaStream_t stream) {
 }  // namespace pc
 
 
-// ================================================================ compacting kernel, second generation (variants 1011...)
-// Same two-stage scheme as `pc` above, with three changes:
-//  * MIXED ROUNDS.  The Body only ever meets the floor, so its step is independent of both legs during the sweep (association
-//    lists, Walker.cs:204-208) and is folded into the first leg phase; and the two list orders (floor first / floor last,
-//    Walker.cs:212-223) no longer get separate rounds: in sub-round a the floor-first walkers queue their floor items while the
-//    floor-last walkers queue their leg-pair items, in sub-round b the other way round.  A round drains a floor queue and a
-//    leg-pair queue back to back (different warps take them), so a substep is 3 joint rounds + 4 sweep rounds = 7 rounds
-//    whatever the mix (before: 8 with one list order in the CTA, 10 with both).
-//  * kG lanes per queued item is a template parameter (2, 4 or 8: the lanes split the SAT axes and the moved vertices).
-//  * the noinline stages rebuild their shared-memory pointers from the extern array instead of receiving generic pointers
-//    (LDS / STS instead of generic LD / ST).
-namespace pm {
-using namespace pl;
-using pc::integrate_body_inl;
-using pc::pair_slot;
-using pc::partner_of;
-using pc::kItemFloor;
-using pc::kItemJoint;
-using pc::kItemPole;
-using pc::kDrainVote;
-
-extern __shared__ __align__(16) unsigned char smem_pm[];
-
-template <int kE>
-struct Shared {
-  float state[(kV2Count * 2 + kFCount) * kE];
-  Material mtab[WB_MAX_MATERIALS];      // copy of the material table (stage 2 works on other walkers: divergent indices)
-  unsigned char wmat[kE], fmat[kE];     // walker / floor material id per walker
-  FloorConst floor;
-  unsigned char axis[4 * kE];   // last separating axis per ordered leg pair {LLL->LLU, LLU->LLL, RLL->RLU, RLU->RLL}
-  unsigned short qf[3 * kE];    // floor items (Body + two leg segments per walker at most) or joint items
-  unsigned short qp[2 * kE];    // leg-pair items
-  int count[2][2];              // [parity][0: qf, 1: qp]; the next round's counters are cleared while the current one drains
-};
-template <int kE> __device__ __forceinline__ Shared<kE>& shm() { return *reinterpret_cast<Shared<kE>*>(smem_pm); }
-
-template <int L, int kE>
-__device__ __forceinline__ void env_for_column(Env<L, kE>& e, int col, bool live) {
-  Shared<kE>& S = shm<kE>();
-  e.v2 = reinterpret_cast<float2*>(S.state) + col;
-  e.f = S.state + kV2Count * kE * 2 + col;
-  e.fl = &S.floor;
-  e.sub = (L == 1) ? 0 : (int)(threadIdx.x % L);
-  e.gsub = e.sub;
-  e.gshift = (L == 1) ? 0 : (int)(((threadIdx.x & 31) / L) * L);
-  e.live = live;
-  e.flags = 0;
-  set_materials(e, S.mtab[S.wmat[col]], S.mtab[S.fmat[col]]);
-}
-
-// queue push: one shared-memory atomic per warp (must be called by all 32 lanes)
-__device__ __forceinline__ void push(unsigned short* queue, int* count, bool want, int item) {
-  const unsigned m = __ballot_sync(kFull, want);
-  if (m == 0) return;
-  const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(count, __popc(m));
-  base = __shfl_sync(kFull, base, 0);
-  if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)item;
-}
-
-// stage 1 of the leg pairs of bodies b0 (left leg) and b1 (right leg) of walker `col`: bit 0 / bit 1 set when the pair needs
-// the full narrow phase.  The cached axis is tested first (a separating axis settles the pair), then the bounding boxes.
-template <int kE>
-__device__ __noinline__ int pole_pairs_need_work(int col, int b0, int b1) {
-  Shared<kE>& S = shm<kE>();
-  const float2* v2 = reinterpret_cast<const float2*>(S.state) + col;
-  int out = 0;
-#pragma unroll 1
-  for (int side = 0; side < 2; side++) {
-    const int A = side ? b1 : b0, B = partner_of(A);
-    const int cached = S.axis[pair_slot(A) * kE + col];
-    float2 PA[6], PB[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) PA[i] = v2[(A * 6 + i) * kE];
-#pragma unroll
-    for (int i = 0; i < 6; i++) PB[i] = v2[(B * 6 + i) * kE];
-    const int own = cached < 6 ? A : B;
-    const int k = cached < 6 ? cached : cached - 6;
-    const float2 p0 = v2[(own * 6 + k) * kE], p1 = v2[(own * 6 + (k == 5 ? 0 : k + 1)) * kE];
-    const float2 edge = vsub(p1, p0);
-    float2 axis = mk2(-edge.y, edge.x);
-    const bool skip = (axis.x == 0.0f) && (axis.y == 0.0f);
-    axis = vnormalize_fast(axis);
-    float amn, amx, bmn, bmx;
-    project6(PA, axis, amn, amx);
-    project6(PB, axis, bmn, bmx);
-    const bool overlapping = (amn < bmx) && (bmn < amx);
-    if (!skip && !overlapping) continue;  // AxisChecks would return false at this axis
-    float2 amin, amax, bmin, bmax;
-    aabb6(PA, amin, amax);
-    aabb6(PB, bmin, bmax);
-    if (aabb_hit(amin, amax, bmin, bmax)) out |= 1 << side;
-  }
-  return out;
-}
-
-// stage 1 of a floor pair: bounding boxes (the caller latches Collided, RigidBody.cs:73-76)
-template <int kE>
-__device__ __forceinline__ bool floor_pair_needs_work(int col, int A) {
-  Shared<kE>& S = shm<kE>();
-  const float2* v2 = reinterpret_cast<const float2*>(S.state) + col;
-  float2 PA[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) PA[i] = v2[(A * 6 + i) * kE];
-  float2 amin, amax;
-  aabb6(PA, amin, amax);
-  return aabb_hit(amin, amax, S.floor.bb_min, S.floor.bb_max);
-}
-
-template <int kE>
-__device__ __noinline__ void integrate_bodies(int col, int b0, int b1, bool with_body, float dt) {
-  Env<1, kE> e;
-  env_for_column<1, kE>(e, col, true);
-  const int nb = with_body ? 3 : 2;
-#pragma unroll 1
-  for (int k = 0; k < nb; k++) integrate_body_inl(e, k == 0 ? b0 : k == 1 ? b1 : BODY, dt);
-}
-
-// stage 2: queued items, densely, kG lanes per item; the warps are rotated by `first_warp` so that the two drains of a mixed
-// round land on different warps.  Item = walker column | payload << 10.
-template <int KIND, int kE, int kG>
-__device__ __noinline__ void drain(const unsigned short* queue, int count, int first_warp) {
-  using EVG = Env<kG, kE>;
-  Shared<kE>& S = shm<kE>();
-  constexpr int kWarps = kE / 32, kPerWarp = 32 / kG;
-  int w = (int)(threadIdx.x >> 5) - first_warp;
-  if (w < 0) w += kWarps;
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int base = w * kPerWarp; base < count; base += kWarps * kPerWarp) {
-    const int slot = base + lane / kG;
-    const bool valid = slot < count;
-    const int item = valid ? queue[slot] : 0;
-    const int col = item & 1023, payload = item >> 10;
-    EVG q;
-    env_for_column<kG, kE>(q, col, valid);
-    if (KIND == kItemPole) {
-      int sep_axis = -1;
-      resolve_pair<EVG, kG, false, false, kDrainVote>(q, valid, payload, partner_of(payload), nullptr, &sep_axis);
-      // a lane that saw a separating axis records it (any separating axis is a valid cache entry)
-      if (valid && sep_axis >= 0) S.axis[pair_slot(payload) * kE + col] = (unsigned char)sep_axis;
-    } else if (KIND == kItemFloor) {
-      resolve_pair<EVG, kG, false, true, kDrainVote>(q, valid, payload, FLOOR, nullptr);
-    } else {
-      const int k = payload;
-      const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
-      joint_step<EVG, false>(q, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, nullptr);
-    }
-  }
-}
-
-template <int kE, int kG>
-__global__ void __launch_bounds__(kE, kE == 192 ? 3 : 512 / kE) physics_compact2_kernel(const PhysicsParams p) {
-  using EV = Env<1, kE>;
-  Shared<kE>& S = shm<kE>();
-  const int tid = threadIdx.x;
-  const int env0 = blockIdx.x * kE;
-  const int env = env0 + tid;
-  const bool live = env < p.n;
-  const int envc = live ? env : 0;
-
-  for (int w = tid; w < (int)(sizeof(FloorConst) / 4); w += kE)
-    reinterpret_cast<uint32_t*>(&S.floor)[w] = reinterpret_cast<const uint32_t*>(&c_floor)[w];
-  // stage the record of my walker (SoA rows are contiguous over walkers: coalesced)
-#pragma unroll 8
-  for (int f = 0; f < 88; f++)
-    S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = live ? p.state[(size_t)f * p.n_pad + env] : c_init_state[f];
-  for (int w = tid; w < (int)(sizeof(Material) * WB_MAX_MATERIALS / 4); w += kE)
-    reinterpret_cast<uint32_t*>(S.mtab)[w] = reinterpret_cast<const uint32_t*>(c_materials)[w];
-  S.wmat[tid] = p.walker_mat[envc];
-  S.fmat[tid] = p.floor_mat[envc];
-#pragma unroll
-  for (int s = 0; s < 4; s++) S.axis[s * kE + tid] = 0;
-  if (tid == 0) S.count[0][0] = S.count[0][1] = S.count[1][0] = S.count[1][1] = 0;
-  __syncthreads();  // the floor constants / counters written above are read by every thread of the CTA
-  EV e;
-  env_for_column<1, kE>(e, tid, live);
-  V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
-  float* torque_rows = p.state + (size_t)88 * p.n_pad + envc;
-  e.flags = p.flags[envc];
-  int steps = p.steps[envc];
-  float2 pos = mk2(p.pos[envc], p.pos[p.n_pad + envc]);
-
-  auto write_initial_record = [&]() {  // Walker.Reset + CreateCreature (own walker only: no synchronisation needed)
-#pragma unroll 1
-    for (int f = 0; f < 88; f++) S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = c_init_state[f];
-    V2(e, BODY * 6 + 5) = V2(e, BODY * 6);
-    for (int k = 0; k < 4; k++) torque_rows[(size_t)k * p.n_pad] = c_init_state[88 + k];
-  };
-
-  if (p.phases & kPhaseResetMasked) {
-    if (live && (p.reset_mask == nullptr || p.reset_mask[envc])) {
-      write_initial_record();
-      e.flags = (p.phases & kPhaseFirstEpisode) ? 0 : WB_FLAG_FLOOR_FIRST;
-      steps = 0;
-      pos = V2(e, kV2Cen + BODY);
-    }
-  }
-  if (p.phases & kPhaseIncSteps) steps++;
-  if ((p.phases & kPhaseTakeActions) && live) {
-    const float4 a4 = *reinterpret_cast<const float4*>(p.actions + (size_t)env * 4);
-    const float act[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      float a = act[k];
-      if (a >= 1.0f) a = 1.0f;
-      else if (a <= -1.0f) a = -1.0f;
-      const float change = fsub(a, torque_rows[(size_t)k * p.n_pad]);
-      torque_rows[(size_t)k * p.n_pad] = a;
-      const int bodyB = (k == 0) ? LLU : (k == 1) ? RLU : (k == 2) ? LLL : RLL;
-      F1(e, kFOmega + bodyB) = fadd(F1(e, kFOmega + bodyB), fmul(change, 5.0f));
-    }
-  }
-
-  if (p.phases & kPhaseStepObjects) {
-    const float dt = fdiv(p.dt, (float)p.iterations);
-    // the list order only changes at a reset, never inside the sweep.  Padding threads (env >= n) sweep a scratch copy of
-    // the initial walker like everybody else -- no thread ever leaves the lockstep -- and never store to global memory.
-    const bool floor_first = (e.flags & WB_FLAG_FLOOR_FIRST) != 0;
-    constexpr int kPerWarp = 32 / kG, kWarps = kE / 32;
-
-    auto joint_gap_active = [&](int k) {
-      const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
-      const float2 ab = vsub(V2(e, B * 6 + (k < 2 ? 4 : 3)), V2(e, A * 6 + (k < 2 ? 1 : 2)));
-      const float depth = fsqrt(fadd(fmul(ab.x, ab.x), fmul(ab.y, ab.y)));
-      return !(depth < 0.1f);
-    };
-    int parity = 0;
-    // one queue round: (stage 1 already pushed) barrier, drain, barrier; the other parity's counters are cleared in between
-    auto joint_round = [&]() {
-      __syncthreads();
-      if (tid == 0) S.count[parity ^ 1][0] = S.count[parity ^ 1][1] = 0;
-      const int cj = S.count[parity][0];
-      if (cj) drain<kItemJoint, kE, kG>(S.qf, cj, 0);
-      __syncthreads();
-      parity ^= 1;
-    };
-    auto sweep_round = [&]() {
-      __syncthreads();
-      if (tid == 0) S.count[parity ^ 1][0] = S.count[parity ^ 1][1] = 0;
-      const int cf = S.count[parity][0], cp = S.count[parity][1];
-      if (cf) drain<kItemFloor, kE, kG>(S.qf, cf, 0);
-      if (cp) drain<kItemPole, kE, kG>(S.qp, cp, ((cf + kPerWarp - 1) / kPerWarp) % kWarps);
-      __syncthreads();
-      parity ^= 1;
-    };
-
-#pragma unroll 1
-    for (int it = 0; it < p.iterations; it++) {
-      // ---- joints in creation order; (Body,RLU) and (LLU,LLL) touch disjoint bodies and share a round
-      push(S.qf, &S.count[parity][0], joint_gap_active(0), tid | (0 << 10));
-      joint_round();
-      push(S.qf, &S.count[parity][0], joint_gap_active(1), tid | (1 << 10));
-      push(S.qf, &S.count[parity][0], joint_gap_active(2), tid | (2 << 10));
-      joint_round();
-      push(S.qf, &S.count[parity][0], joint_gap_active(3), tid | (3 << 10));
-      joint_round();
-      // ---- body sweep: {LLL, RLL, Body}, then {LLU, RLU}; per leg segment [floor | leg partner] in the walker's list order
-#pragma unroll 1
-      for (int ph = 0; ph < 2; ph++) {
-        const int b0 = ph == 0 ? LLL : LLU;
-        const int b1 = ph == 0 ? RLL : RLU;
-        integrate_bodies<kE>(tid, b0, b1, ph == 0, dt);
-#pragma unroll 1
-        for (int sub = 0; sub < 2; sub++) {
-          bool f0 = false, f1 = false, fb = false;
-          int pp = 0;
-          if ((sub == 0) == floor_first) {
-            f0 = floor_pair_needs_work<kE>(tid, b0);
-            f1 = floor_pair_needs_work<kE>(tid, b1);
-            if (f0) e.flags |= 1 << b0;  // if (body._isFloor) Collided = true  (before SAT: RigidBody.cs:75)
-            if (f1) e.flags |= 1 << b1;
-          } else {
-            pp = pole_pairs_need_work<kE>(tid, b0, b1);
-          }
-          if (ph == 0 && sub == 0) {
-            fb = floor_pair_needs_work<kE>(tid, BODY);
-            if (fb) e.flags |= 1 << BODY;
-          }
-          push(S.qf, &S.count[parity][0], f0, tid | (b0 << 10));
-          push(S.qf, &S.count[parity][0], f1, tid | (b1 << 10));
-          if (ph == 0 && sub == 0) push(S.qf, &S.count[parity][0], fb, tid | (BODY << 10));
-          push(S.qp, &S.count[parity][1], (pp & 1) != 0, tid | (b0 << 10));
-          push(S.qp, &S.count[parity][1], (pp & 2) != 0, tid | (b1 << 10));
-          sweep_round();
-        }
-      }
-    }
-  }
-
-  if (p.phases & kPhaseObserve) {
-    const float2 prev = pos;
-    pos = V2(e, kV2Cen + BODY);
-    if (e.flags & ((1 << BODY) | (1 << LLU) | (1 << RLU))) e.flags |= WB_FLAG_TERMINAL;
-    const float dx = fsub(pos.x, prev.x);
-    const float h = fdiv(V2(e, BODY * 6 + 1).y, 500.0f);
-    float r = 0.0f;
-    r = fadd(r, (dx > 0.0f && h < 1.6f) ? dx : 0.0f);
-    r = fsub(r, (h > 1.65f) ? -0.1f : 0.0f);
-    bool terminal = false;
-    if ((e.flags & WB_FLAG_TERMINAL) || steps > p.max_timesteps) {
-      if (e.flags & WB_FLAG_TERMINAL) r = fsub(r, 40.0f);
-      terminal = true;
-    }
-    if (pos.x > 900.0f) {
-      r = fadd(r, 80.0f);
-      terminal = true;
-    }
-    if (live && terminal && (p.phases & kPhaseAutoReset)) {
-      write_initial_record();
-      e.flags = WB_FLAG_FLOOR_FIRST;
-      steps = 0;
-      pos = V2(e, kV2Cen + BODY);
-    }
-    if (live) {
-      store_observation(e, p.obs + (size_t)env * WB_OBS);
-      p.reward[env] = r;
-      p.done[env] = terminal ? 1 : 0;
-    }
-  } else if (p.phases & kPhaseObsOnly) {
-    if (live) store_observation(e, p.obs + (size_t)env * WB_OBS);
-  }
-
-  if (live) {
-    p.flags[env] = e.flags;
-    p.steps[env] = steps;
-    p.pos[env] = pos.x;
-    p.pos[p.n_pad + env] = pos.y;
-#pragma unroll 8
-    for (int f = 0; f < 88; f++) p.state[(size_t)f * p.n_pad + env] = S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)];
-  }
-}
-
-template <int kE, int kG>
-static cudaError_t launch_compact2(const PhysicsParams& p, cudaStream_t stream) {
-  // opt in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute (a process may drive several GPUs)
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(physics_compact2_kernel<kE, kG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared<kE>));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(physics_compact2_kernel<kE, kG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    if (getenv("WB_DEBUG_OCCUPANCY")) {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, physics_compact2_kernel<kE, kG>, kE, sizeof(Shared<kE>));
-      fprintf(stderr, "physics_compact2_kernel<%d,%d>: %d CTAs/SM, %zu B shared per CTA\n", kE, kG, nb, sizeof(Shared<kE>));
-    }
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
-  physics_compact2_kernel<kE, kG><<<(p.n + kE - 1) / kE, kE, sizeof(Shared<kE>), stream>>>(p);
-  return cudaGetLastError();
-}
-
-}  // namespace pm
-
 
 // ---------------------------------------------------------------- host side
 cudaError_t upload_materials(const Material* table, int count) {
@@ -1707,8 +1349,7 @@ cudaError_t upload_scene_constants(const float* init_state92, const FloorConst* 
 // of 128 walkers, kept for comparison)
 bool physics_lanes_supported(int variant) {
   switch (variant) {
-    case 1: case 2: case 4: case 8: case 16: case 32: case 104: case 108: case 116: case 1001: case 1002: case 1003: case 1004: case 1016:
-    case 1011: case 1012: case 1013: case 1014: case 1015: return true;
+    case 1: case 2: case 4: case 8: case 16: case 32: case 104: case 108: case 116: case 1001: case 1002: case 1003: return true;
     default: return false;
   }
 }
@@ -1728,14 +1369,6 @@ cudaError_t launch_physics(const PhysicsParams& p, int variant, bool trace, cuda
     case 1001: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<256>(p, stream);
     case 1002: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<32>(p, stream);
     case 1003: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<128>(p, stream);
-    case 1004: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<192>(p, stream);
-    case 1016: return trace ? pl::launch_l<1, 1>(p, true, stream) : pm::launch_compact2<192, 2>(p, stream);
-    // second-generation compacting kernels (mixed rounds): <lockstep scope, lanes per queued item>
-    case 1011: return trace ? pl::launch_l<1, 1>(p, true, stream) : pm::launch_compact2<256, 2>(p, stream);
-    case 1012: return trace ? pl::launch_l<1, 1>(p, true, stream) : pm::launch_compact2<256, 4>(p, stream);
-    case 1013: return trace ? pl::launch_l<1, 1>(p, true, stream) : pm::launch_compact2<256, 8>(p, stream);
-    case 1014: return trace ? pl::launch_l<1, 1>(p, true, stream) : pm::launch_compact2<128, 4>(p, stream);
-    case 1015: return trace ? pl::launch_l<1, 1>(p, true, stream) : pm::launch_compact2<512, 4>(p, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -126,7 +126,7 @@ def test_user_material_plugin(gpu, O):
     assert_state_equal(env, ref, "custom material")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 4, 1001, 1002, 1011, 1012])
+@pytest.mark.parametrize("variant", [0, 1, 4, 1001, 1002])
 def test_ragged_batch_sizes(gpu, O, variant):
     """Batch sizes that leave partially filled warps / CTAs / SoA padding, for the auto-selected kernel and explicit variants."""
     for n in (1, 7, 9, 33, 300):
@@ -148,6 +148,29 @@ def test_nonfinite_and_out_of_range_actions_are_clipped_like_matrix_clip(gpu, O)
     env.step(a)
     ref.step(a)
     assert_state_equal(env, ref, "clip")
+
+
+def test_pinned_host_buffers_zero_copy_path_matches_oracle(gpu, O):
+    """wb_env_step with PINNED host buffers: the kernel reads the actions and writes obs / reward / done straight through the
+    device aliases of the caller's buffers (no staging copies).  Same bits as the oracle, and as the staged path."""
+    import torch
+    n = 300
+    env = gpu.EnvBatch(n, floor_materials=[MATS[i % 8] for i in range(n)])
+    staged = gpu.EnvBatch(n, floor_materials=[MATS[i % 8] for i in range(n)])
+    ref = O.EnvBatch(n, floor=[MATS[i % 8] for i in range(n)])
+    a_pin = torch.empty(n, 4).pin_memory()
+    obs, rew, done = torch.empty(n, 12).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    out = (obs.numpy(), rew.numpy(), done.numpy())
+    rng = np.random.default_rng(11)
+    for t in range(30):
+        a = rng.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+        a_pin.copy_(torch.from_numpy(a))
+        env.step(a_pin, out=out)
+        sobs, srew, sdone = staged.step(a)  # pageable numpy buffers: staged copies
+        robs, rrew, rdone = ref.step(a)
+        assert np.array_equal(bits(out[0]), bits(robs)) and np.array_equal(bits(out[1]), bits(rrew)) and np.array_equal(out[2], rdone), f"step {t}"
+        assert np.array_equal(bits(sobs), bits(robs)) and np.array_equal(bits(srew), bits(rrew)) and np.array_equal(sdone, rdone)
+    assert_state_equal(env, ref, "zero-copy path")
 
 
 def test_committed_golden_rollout(gpu):
@@ -228,7 +251,7 @@ def test_rotation_coefficients_match_libm_rounded_to_float(gpu, O, mode):
         assert bad_c == 0 and bad_s == 0
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32, 104, 108, 116, 1001, 1002, 1003, 1004, 1011, 1012, 1013, 1014, 1015, 1016])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32, 104, 108, 116, 1001, 1002, 1003])
 def test_kernel_variants_bit_exact(gpu, O, lanes):
     """Both thread mappings (two envs per warp / one env per warp) against the oracle, traces included."""
     n = 40
