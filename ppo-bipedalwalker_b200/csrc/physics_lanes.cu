@@ -973,6 +973,11 @@ struct Shared {
   unsigned short queue[2 * kE];
   int count[2];  // ping-pong: the counter of the next round is cleared while the current one drains
 };
+// The noinline stages below rebuild their shared-memory pointers from this array instead of receiving pointers as arguments:
+// an argument is a generic 64-bit address (LD / ST through the generic path), a pointer derived here stays LDS / STS.
+extern __shared__ __align__(16) unsigned char smem_pc[];
+template <int kE> __device__ __forceinline__ Shared<kE>& shm() { return *reinterpret_cast<Shared<kE>*>(smem_pc); }
+
 template <int kE> __device__ __forceinline__ void scope_sync() {
   if (kE == 32) __syncwarp(); else __syncthreads();
 }
@@ -1006,10 +1011,16 @@ __device__ __forceinline__ void push(Shared<kE>& S, int parity, bool want, int i
   if (want) S.queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)item;
 }
 
+__device__ __forceinline__ int pair_slot(int b) { return b == LLL ? 0 : b == LLU ? 1 : b == RLL ? 2 : 3; }
+__device__ __forceinline__ int partner_of(int b) { return (0x34F01 >> (4 * b)) & 0xF; }  // {LLU, LLL, -, RLU, RLL}
+
 // stage 1 of a leg pair: true when the pair needs the full narrow phase.  Tests the cached axis first (a separating axis
 // settles the pair: no collision, nothing else to do), then the bounding boxes.
-template <class EV>
-__device__ __noinline__ bool pole_pair_needs_work(const EV& e, int A, int B, int cached) {
+template <int kE>
+__device__ __noinline__ bool pole_pair_needs_work(int col, int A, int B) {
+  Env<1, kE> e;
+  env_for_column(e, shm<kE>(), col, true);
+  const int cached = shm<kE>().axis[pair_slot(A) * kE + col];
   float2 PA[6], PB[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) PA[i] = V2(e, A * 6 + i);
@@ -1033,17 +1044,17 @@ __device__ __noinline__ bool pole_pair_needs_work(const EV& e, int A, int B, int
   return aabb_hit(amin, amax, bmin, bmax);
 }
 
-// stage 1 of a floor pair: bounding boxes + the Collided latch (RigidBody.cs:73-76)
-template <class EV>
-__device__ __noinline__ bool floor_pair_needs_work(EV& e, int A) {
+// stage 1 of a floor pair: bounding boxes (the caller latches Collided, RigidBody.cs:73-76)
+template <int kE>
+__device__ __noinline__ bool floor_pair_needs_work(int col, int A) {
+  Env<1, kE> e;
+  env_for_column(e, shm<kE>(), col, true);
   float2 PA[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) PA[i] = V2(e, A * 6 + i);
   float2 amin, amax;
   aabb6(PA, amin, amax);
-  const bool hit = aabb_hit(amin, amax, e.fl->bb_min, e.fl->bb_max);
-  if (hit) e.flags |= (1 << A);
-  return hit;
+  return aabb_hit(amin, amax, e.fl->bb_min, e.fl->bb_max);
 }
 
 // RigidBody.StepLinearVelocity / StepAngularVelocity / Skeleton.Move / Rotate of one body (the first half of body_step)
@@ -1075,11 +1086,13 @@ __device__ __forceinline__ void integrate_body_inl(const EV& e, int b, float dt)
   V2(e, kV2Vel + b) = v;
   F1(e, kFAngle + b) = ang;
 }
-template <class EV>
-__device__ __noinline__ void integrate_body(const EV& e, int b, float dt) { integrate_body_inl(e, b, dt); }
+template <int kE>
+__device__ __noinline__ void integrate_body(int col, int b, float dt) {
+  Env<1, kE> e;
+  env_for_column(e, shm<kE>(), col, true);
+  integrate_body_inl(e, b, dt);
+}
 
-__device__ __forceinline__ int pair_slot(int b) { return b == LLL ? 0 : b == LLU ? 1 : b == RLL ? 2 : 3; }
-__device__ __forceinline__ int partner_of(int b) { return (0x34F01 >> (4 * b)) & 0xF; }  // {LLU, LLL, -, RLU, RLL}
 
 enum { kItemPole = 0, kItemFloor = 1, kItemJoint = 2 };
 // SAT rounds of the queued items: 16 items share a warp, so an early stop (all of them separated) practically never happens
@@ -1107,7 +1120,8 @@ __device__ __forceinline__ void group_env_for_column(Env<kG, kE>& e, Shared<kE>&
 }
 
 template <int KIND, int kE>
-__device__ __noinline__ void drain(Shared<kE>& S, int parity) {
+__device__ __noinline__ void drain(int parity) {
+  Shared<kE>& S = shm<kE>();
   using EVG = Env<kG, kE>;
   const int count = S.count[parity];
   const int warp_base = (threadIdx.x >> 5) * (32 / kG), lane = threadIdx.x & 31;
@@ -1137,8 +1151,7 @@ __device__ __noinline__ void drain(Shared<kE>& S, int parity) {
 template <int kE>
 __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const PhysicsParams p) {
   using EV = Env<1, kE>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Shared<kE>& S = *reinterpret_cast<Shared<kE>*>(smem_raw);
+  Shared<kE>& S = shm<kE>();
   const int tid = threadIdx.x;
   const int env0 = blockIdx.x * kE;
   const int env = env0 + tid;
@@ -1227,37 +1240,43 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
     for (int it = 0; it < p.iterations; it++) {
       // ---- joints in creation order; (Body,RLU) and (LLU,LLL) touch disjoint bodies and share a round
       push(S, parity, joint_gap_active(0), tid | (0 << 10));
-      round([&] { drain<kItemJoint, kE>(S, parity); });
+      round([&] { drain<kItemJoint, kE>(parity); });
       push(S, parity, joint_gap_active(1), tid | (1 << 10));
       push(S, parity, joint_gap_active(2), tid | (2 << 10));
-      round([&] { drain<kItemJoint, kE>(S, parity); });
+      round([&] { drain<kItemJoint, kE>(parity); });
       push(S, parity, joint_gap_active(3), tid | (3 << 10));
-      round([&] { drain<kItemJoint, kE>(S, parity); });
+      round([&] { drain<kItemJoint, kE>(parity); });
       // ---- body sweep: {LLL, RLL}, {LLU, RLU}, {Body}; per body [floor if floor-first] [leg partner] [floor if floor-last]
 #pragma unroll 1
       for (int ph = 0; ph < 3; ph++) {
         const int b0 = ph == 0 ? LLL : ph == 1 ? LLU : BODY;
         const int b1 = ph == 0 ? RLL : RLU;
         const int nb = ph == 2 ? 1 : 2;
-        integrate_body(e, b0, dt);
-        if (nb == 2) integrate_body(e, b1, dt);
+        integrate_body<kE>(tid, b0, dt);
+        if (nb == 2) integrate_body<kE>(tid, b1, dt);
         if (ph == 2) {
-          push(S, parity, floor_pair_needs_work(e, BODY), tid | (BODY << 10));
-          round([&] { drain<kItemFloor, kE>(S, parity); });
+          const bool fb = floor_pair_needs_work<kE>(tid, BODY);
+          if (fb) e.flags |= 1 << BODY;
+          push(S, parity, fb, tid | (BODY << 10));
+          round([&] { drain<kItemFloor, kE>(parity); });
           continue;
         }
         if (any_first) {
-          push(S, parity, floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 10));
-          push(S, parity, floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 10));
-          round([&] { drain<kItemFloor, kE>(S, parity); });
+          const bool f0 = floor_first && floor_pair_needs_work<kE>(tid, b0), f1 = floor_first && floor_pair_needs_work<kE>(tid, b1);
+          e.flags |= (f0 ? 1 << b0 : 0) | (f1 ? 1 << b1 : 0);
+          push(S, parity, f0, tid | (b0 << 10));
+          push(S, parity, f1, tid | (b1 << 10));
+          round([&] { drain<kItemFloor, kE>(parity); });
         }
-        push(S, parity, pole_pair_needs_work(e, b0, partner_of(b0), S.axis[pair_slot(b0) * kE + tid]), tid | (b0 << 10));
-        push(S, parity, pole_pair_needs_work(e, b1, partner_of(b1), S.axis[pair_slot(b1) * kE + tid]), tid | (b1 << 10));
-        round([&] { drain<kItemPole, kE>(S, parity); });
+        push(S, parity, pole_pair_needs_work<kE>(tid, b0, partner_of(b0)), tid | (b0 << 10));
+        push(S, parity, pole_pair_needs_work<kE>(tid, b1, partner_of(b1)), tid | (b1 << 10));
+        round([&] { drain<kItemPole, kE>(parity); });
         if (any_last) {
-          push(S, parity, !floor_first && floor_pair_needs_work(e, b0), tid | (b0 << 10));
-          push(S, parity, !floor_first && floor_pair_needs_work(e, b1), tid | (b1 << 10));
-          round([&] { drain<kItemFloor, kE>(S, parity); });
+          const bool f0 = !floor_first && floor_pair_needs_work<kE>(tid, b0), f1 = !floor_first && floor_pair_needs_work<kE>(tid, b1);
+          e.flags |= (f0 ? 1 << b0 : 0) | (f1 ? 1 << b1 : 0);
+          push(S, parity, f0, tid | (b0 << 10));
+          push(S, parity, f1, tid | (b1 << 10));
+          round([&] { drain<kItemFloor, kE>(parity); });
         }
       }
     }
