@@ -14,6 +14,9 @@ construction all walkers are identical, which flatters a SIMT kernel: no diverge
 
 Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps an L2 flush (256 MiB
 memset) runs OUTSIDE the event pairs; ms_per_step = sum of the K event intervals / K, max over ranks.
+"e2e" = the same step through the public host-buffer call (EnvBatch.step -> wb_env_step) with pinned host actions in and host
+obs/reward/done out every step, wall clock around the call (the bytes cross PCIe inside the timed region: read and written by
+the kernel itself through the pinned buffers' device aliases -- the zero-copy path -- instead of staged copies).
 Extra keys: "at_scale" = the same step on 262144 walkers per GPU (device-resident, the throughput regime the north-star
 target is phrased in); "secondary" = PPO samples/s (configs[2]).
 """
@@ -344,7 +347,9 @@ def run_ours(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": world * n / (e2e_ms_step * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 16,
-                    "d2h_bytes_per_step": n * (48 + 4 + 1), "ms_per_step": e2e_ms_step},
+                    "d2h_bytes_per_step": n * (48 + 4 + 1), "ms_per_step": e2e_ms_step,
+                    "path": "EnvBatch.step -> wb_env_step with pinned host buffers: the kernel reads the actions and writes "
+                            "obs/reward/done through the buffers' device aliases (zero-copy over PCIe), one stream sync per step"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": ncu_traffic("physics_lanes_kernel_4096"),

@@ -132,12 +132,20 @@ int32_t wb_env_get_obs(wb_env_batch* env, float* obs_host);
 
 /* Environment.Update minus the policy (Environment.cs:64-92): _steps++, TakeActions(Clip(a)), Step, and when
  * auto_reset != 0 the Reset + InitialState that follows a terminal step (the returned obs is then the
- * initial observation).  One fused kernel launch; host buffers, H2D/D2H inside the call. */
+ * initial observation).  One fused kernel launch; host buffers.  When every buffer of the call is page-locked
+ * (cudaHostAlloc / cudaHostRegister / wb_host_pin) the kernel reads the actions and writes obs / reward / done directly
+ * through the device-side aliases of the caller's buffers (zero-copy: no staging copies, one synchronisation); pageable
+ * buffers take H2D copy + launch + D2H copies.  The results are identical. */
 int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_time, int32_t auto_reset, float* obs_host,
                     float* reward_host, uint8_t* done_host);
 /* device-pointer variant: enqueue only (no copies, no sync) */
 int32_t wb_env_step_dev(wb_env_batch* env, const float* actions_dev, float delta_time, int32_t auto_reset, float* obs_dev,
                         float* reward_dev, uint8_t* done_dev);
+/* Page-lock / release a host buffer the caller owns (e.g. a pinned GCHandle of a C# array: the reference keeps its
+ * observation / action Matrix objects on the managed heap, Environment.cs:64-92) so that wb_env_step takes the zero-copy
+ * path.  The buffer must stay allocated and un-moved until wb_host_unpin. */
+int32_t wb_host_pin(void* host_ptr, size_t bytes);
+int32_t wb_host_unpin(void* host_ptr);
 /* number of kernel launches this handle has issued (bench.py "gpu_launches") */
 int32_t wb_env_launch_count(const wb_env_batch* env, int64_t* count_out);
 /* physics kernel variant: 2, 4, 8 or 16 lanes per walker (the lanes split the two legs, the SAT axes and the vertices: latency,

@@ -3,7 +3,8 @@ Environment / Walker / IMaterial / PPOAgent method surface.  Imported as `ppo_bi
 (see __graft_entry__.load_package); the compute lives in lib/libwalker_b200.so (csrc/), never in Python."""
 from ._lib import Hyperparams, WalkerB200Error, declared_symbols, lib  # noqa: F401
 from .env import (DT_FRAME, MATERIALS, Carpet, EnvBatch, Environment, Ice, IMaterial, Metal, Paper, Rubber,  # noqa: F401
-                  SuperRubber, Titanium, Walker, Wood, default_hyperparams, init, JOINT_TRACE_DTYPE, PAIR_TRACE_DTYPE)
+                  SuperRubber, Titanium, Walker, Wood, default_hyperparams, init, pin_host, unpin_host, JOINT_TRACE_DTYPE,
+                  PAIR_TRACE_DTYPE)
 
 from . import dist  # noqa: F401
 from .ppo import *  # noqa: F401,F403

@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         "wb_env_step": (C.c_int32, [vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
         "wb_env_step_dev": (C.c_int32, [vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
         "wb_env_launch_count": (C.c_int32, [vp, i64p]),
+        "wb_host_pin": (C.c_int32, [vp, C.c_size_t]),
+        "wb_host_unpin": (C.c_int32, [vp]),
         "wb_env_set_variant": (C.c_int32, [vp, C.c_int32]),
         "wb_env_get_variant": (C.c_int32, [vp, ip]),
         "wb_debug_rotz": (C.c_int32, [C.c_int32, vp, C.c_int32, vp, vp]),

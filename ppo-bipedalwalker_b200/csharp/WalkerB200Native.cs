@@ -50,6 +50,10 @@ public static class Wb
     [DllImport(Lib)] public static extern int wb_env_observe(IntPtr env, float[] obs, float[] reward, byte[] done);
     [DllImport(Lib)] public static extern int wb_env_get_obs(IntPtr env, float[] obs);                            // Walker.GetState
     [DllImport(Lib)] public static extern int wb_env_step(IntPtr env, float[] actions, float deltaTime, int autoReset, float[] obs, float[] reward, byte[] done);
+    // pinned-pointer overload + page-locking: with GCHandle-pinned arrays registered through wb_host_pin the step is zero-copy
+    [DllImport(Lib, EntryPoint = "wb_env_step")] public static extern int wb_env_step_pinned(IntPtr env, IntPtr actions, float deltaTime, int autoReset, IntPtr obs, IntPtr reward, IntPtr done);
+    [DllImport(Lib)] public static extern int wb_host_pin(IntPtr hostPtr, UIntPtr bytes);
+    [DllImport(Lib)] public static extern int wb_host_unpin(IntPtr hostPtr);
 
     // PPOAgent / NeuralNetwork / Matrix (Walker/PPO/)
     [DllImport(Lib)] public static extern int wb_policy_create(int stateSize, int actionSize, int[] actorKinds, int[] actorSizes, int actorLayers,

@@ -525,6 +525,20 @@ int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_ti
   return copy_out(env, obs_host, reward_host, done_host);
 }
 
+int32_t wb_host_pin(void* host_ptr, size_t bytes) {
+  WB_REQUIRE(host_ptr && bytes > 0, "bad argument");
+  if (int32_t rc = require_device()) return rc;
+  WB_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault));
+  return WB_OK;
+}
+
+int32_t wb_host_unpin(void* host_ptr) {
+  WB_REQUIRE(host_ptr, "null argument");
+  if (int32_t rc = require_device()) return rc;
+  WB_CUDA(cudaHostUnregister(host_ptr));
+  return WB_OK;
+}
+
 int32_t wb_env_step_dev(wb_env_batch* env, const float* actions_dev, float delta_time, int32_t auto_reset, float* obs_dev,
                         float* reward_dev, uint8_t* done_dev) {
   WB_REQUIRE(env && actions_dev && obs_dev && reward_dev && done_dev, "null argument");

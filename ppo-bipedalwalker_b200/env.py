@@ -79,6 +79,18 @@ def _material_ids(spec, n: int):
     return np.asarray(arr, np.uint8)
 
 
+def pin_host(array: np.ndarray) -> np.ndarray:
+    """Page-lock a C-contiguous numpy array in place (wb_host_pin) so that EnvBatch.step takes the zero-copy path for it.
+    Call unpin_host before the array is freed."""
+    assert array.flags["C_CONTIGUOUS"]
+    check(lib().wb_host_pin(ptr(array), array.nbytes))
+    return array
+
+
+def unpin_host(array: np.ndarray) -> None:
+    check(lib().wb_host_unpin(ptr(array)))
+
+
 class EnvBatch:
     """N independent environments resident on the GPU (wb_env_batch handle)."""
 

@@ -173,6 +173,38 @@ def test_pinned_host_buffers_zero_copy_path_matches_oracle(gpu, O):
     assert_state_equal(env, ref, "zero-copy path")
 
 
+def test_host_pin_makes_numpy_buffers_zero_copy(gpu, O):
+    """wb_host_pin / wb_host_unpin (what the C# shim does with its GCHandle-pinned arrays): registered numpy buffers take the
+    zero-copy path of wb_env_step and give the oracle's bits."""
+    n = 64
+    env = gpu.EnvBatch(n)
+    ref = O.EnvBatch(n)
+    # page-aligned so that registering one buffer never overlaps another one's pages
+    def aligned(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        raw = np.empty(nbytes + 8192, np.uint8)
+        off = (-raw.ctypes.data) % 4096
+        return raw[off:off + ((nbytes + 4095) // 4096) * 4096][:nbytes].view(dtype).reshape(shape), raw
+    a, _ka = aligned((n, 4), np.float32)
+    obs, _ko = aligned((n, 12), np.float32)
+    rew, _kr = aligned((n,), np.float32)
+    done, _kd = aligned((n,), np.uint8)
+    bufs = [a, obs, rew, done]
+    for b in bufs:
+        gpu.pin_host(b)
+    try:
+        rng = np.random.default_rng(3)
+        for t in range(10):
+            a[:] = rng.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+            env.step(a, out=(obs, rew, done))
+            robs, rrew, rdone = ref.step(a.copy())
+            assert np.array_equal(bits(obs), bits(robs)) and np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone), f"step {t}"
+    finally:
+        for b in bufs:
+            gpu.unpin_host(b)
+    assert_state_equal(env, ref, "host_pin path")
+
+
 def test_committed_golden_rollout(gpu):
     """The CUDA path against the committed fixture (tests/golden/physics_rollout.npz): no oracle at run time."""
     import os
