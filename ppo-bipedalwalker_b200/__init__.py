@@ -9,5 +9,6 @@ from .env import (DT_FRAME, MATERIALS, Carpet, EnvBatch, Environment, Ice, IMate
 from . import dist  # noqa: F401
 from .ppo import *  # noqa: F401,F403
 from .loop import VectorPPO  # noqa: F401
-from .scene import Hexagon, Hull, IObject, Joint, Pole, Scene, Square, Triangle  # noqa: F401
+from .scene import (CreateCreature, CreateFloor, CreateRoughFloor, Hexagon, Hull, IObject, Joint, Pole, Scene, Square,  # noqa: F401
+                    Triangle)
 from .settings import DeserializeJson, SerializeJson, Settings  # noqa: F401

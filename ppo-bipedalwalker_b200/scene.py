@@ -27,7 +27,7 @@ def _material_id(m) -> int:
     return int(m)
 
 
-@dataclass
+@dataclass(eq=False)  # bodies are compared by identity (like the reference's object references), never by vertex values
 class IObject:
     """One rigid body of a scene: RigidBody ctor arguments (RigidBody.cs:36-50) + its vertex list (Skeleton.AddVectors)."""
     vertices: np.ndarray  # [n, 2] float32
@@ -97,7 +97,7 @@ class Hull:
         return _obj(positions, material, isStatic, isFloor)
 
 
-@dataclass
+@dataclass(eq=False)
 class Joint:
     """new Joint(bodyA, bodyB, indexA, indexB), Joint.cs:20-28 (bodies given as IObjects of the scene)."""
     bodyA: IObject
@@ -165,4 +165,57 @@ class Scene:
         check(lib().wb_scene_step_objects(self._h, C.c_float(deltaTime)))
 
 
-__all__ = ["IObject", "Square", "Triangle", "Hexagon", "Pole", "Hull", "Joint", "Scene"]
+# ---------------------------------------------------------------- the reference's own scene pieces as IObject lists
+def CreateFloor(material="Metal") -> list:
+    """Environment.CreateFloor, flat branch (Environment.cs:211-226): one static floor hull."""
+    return [Hull.FromPositions(material, [(-50, 1050), (-50, 900), (1050, 900), (1050, 1050)], isStatic=True, isFloor=True)]
+
+
+def CreateRoughFloor(heights, segments: int = 10, roughness: int = 100, material="Metal") -> list:
+    """Environment.CreateRoughFloor (Environment.cs:230-261): `segments` static floor hulls whose tops follow random heights.
+    The reference draws them from an UNSEEDED System.Random (`random.Next(0, roughness)`, :242,:249), so the draws are an
+    argument here: heights[0] is the draw for the first `previousVector`, heights[1 + i] the draw of segment i (integers in
+    [0, roughness)).  The reference's invalid-argument branch (segments <= 0 or roughness < 0: log and retry with the
+    defaults) becomes a ValueError."""
+    if segments <= 0 or roughness < 0:
+        raise ValueError("Invalid floor segments/roughness values.")
+    heights = [int(h) for h in heights]
+    if len(heights) != segments + 1 or any(h < 0 or h >= max(roughness, 1) for h in heights):
+        raise ValueError("heights must hold segments + 1 integers in [0, roughness)")
+    initial_y, initial_x = 800, -50
+    prev = (initial_x, initial_y + heights[0])
+    movement = 1200 // segments  # C# integer division
+    out = []
+    for i in range(segments):
+        x = initial_x + i * movement
+        y = 800 + heights[1 + i]
+        out.append(Hull.FromPositions(material, [(x, 1050), prev, (x, y), (x + movement, 1050)], isStatic=True, isFloor=True))
+        prev = (x, y)
+    return out
+
+
+def CreateCreature(position=(125, 800), material="Carpet"):
+    """Walker.CreateCreature (Walker.cs:40-46): CreateBodies (:155-178), CreateJoints (:181-189), AddAssociatedBodies (:204-209)
+    and AddAcceleration((0, 980)).  Returns (objects in the order they join Environment._rigidBodies -- LLL, LLU, Body, RLL,
+    RLU --, joints in creation order)."""
+    px, py = f32(position[0]), f32(position[1])
+    body = Hull.FromPositions(material, [(px + f32(20), py + f32(20)), (px, py + f32(20)), (px - f32(20), py + f32(20)),
+                                         (px - f32(20), py - f32(20)), (px + f32(20), py - f32(20))])
+    body.inverseInertia = 0.0003  # Body.SetInverseInertia(0.0003f), Walker.cs:168
+    llu = Pole.FromSize(material, (px, py + f32(30)), 75)
+    lll = Pole.FromSize(material, (px, py + f32(60)), 75)
+    rlu = Pole.FromSize(material, (px, py + f32(30)), 75)
+    rll = Pole.FromSize(material, (px, py + f32(60)), 75)
+    joints = [Joint(body, llu, 1, 4), Joint(body, rlu, 1, 4), Joint(llu, lll, 2, 3), Joint(rlu, rll, 2, 3)]
+    llu.associated = [rlu, rll, body]
+    lll.associated = [rlu, rll, body]
+    rlu.associated = [llu, lll, body]
+    rll.associated = [llu, lll, body]
+    body.associated = [llu, rlu, lll, rll]
+    objs = [lll, llu, body, rll, rlu]
+    for o in objs:
+        o.acceleration = (0.0, 980.0)
+    return objs, joints
+
+
+__all__ = ["IObject", "Square", "Triangle", "Hexagon", "Pole", "Hull", "Joint", "Scene", "CreateFloor", "CreateRoughFloor", "CreateCreature"]

@@ -106,3 +106,37 @@ def test_iobject_shape_factories_match_the_numpy_restatement(wb, O):
         ref = np.array([(v.x, v.y) for v in b.skeleton.vectors], np.float32)
         assert o.vertices.shape == ref.shape and np.array_equal(o.vertices.view(np.uint32), ref.view(np.uint32))
     assert pairs[-1][0].vertices.shape == (16, 2)  # the largest polygon a scene accepts
+
+
+def test_reference_scene_pieces_match_the_numpy_restatement(wb, O):
+    """CreateCreature (Walker.cs:40-46,155-209), CreateFloor and CreateRoughFloor (Environment.cs:211-261) as IObject lists: same
+    vertices, list order, joint topology and association lists as the NumPy restatement / the reference source."""
+    import np_oracle as P
+    env = P.Environment()
+    objs, joints = wb.CreateCreature()
+    assert len(objs) == 5 and len(joints) == 4
+    for o, b in zip(objs, env.dyn()):
+        ref = np.array([(v.x, v.y) for v in b.skeleton.vectors], np.float32)
+        assert np.array_equal(o.vertices.view(np.uint32), ref.view(np.uint32))
+        assert sorted(objs.index(a) for a in o.associated) == sorted(env.dyn().index(a) for a in b.associated)
+        assert o.acceleration == (0.0, 980.0)
+    assert objs[2].inverseInertia == 0.0003 and all(o.inverseInertia < 0 for i, o in enumerate(objs) if i != 2)
+    for j, rj in zip(joints, env.joints):
+        assert (objs.index(j.bodyA), objs.index(j.bodyB), j.indexA, j.indexB) == (env.dyn().index(rj.a), env.dyn().index(rj.b), rj.ia, rj.ib)
+    floor = wb.CreateFloor()
+    assert len(floor) == 1 and floor[0].isStatic and floor[0].isFloor
+    assert np.array_equal(floor[0].vertices, np.array([(v.x, v.y) for v in env.floor.skeleton.vectors], np.float32))
+    # rough floor: Environment.cs:236-259 by hand for two segments
+    heights = [7, 93, 0, 55, 12, 99, 31, 64, 8, 77, 40]
+    rough = wb.CreateRoughFloor(heights)
+    assert len(rough) == 10 and all(o.isStatic and o.isFloor and o.vertices.shape == (4, 2) for o in rough)
+    assert rough[0].vertices.tolist() == [[-50, 1050], [-50, 807], [-50, 893], [70, 1050]]
+    assert rough[1].vertices.tolist() == [[70, 1050], [-50, 893], [70, 800], [190, 1050]]
+    assert rough[9].vertices.tolist() == [[1030, 1050], [910, 877], [1030, 840], [1150, 1050]]
+    for bad in (lambda: wb.CreateRoughFloor(heights, segments=0), lambda: wb.CreateRoughFloor(heights[:-1]),
+                lambda: wb.CreateRoughFloor([100] + heights[1:])):
+        try:
+            bad()
+            raise AssertionError("accepted an invalid rough floor")
+        except ValueError:
+            pass

@@ -108,3 +108,73 @@ def test_scene_rejects_bad_descriptions(gpu):
         gpu.Scene(1, [tri] * 17)
     with pytest.raises(gpu.WalkerB200Error):
         gpu.Scene(1, [tri, gpu.Square.FromSize("Wood", (5, 5), 4)], [gpu.Joint(tri, tri, 0, 7)])
+
+
+def _oracle_walker_scene(P, floor_bodies, floor_first=False):
+    """The NumPy restatement's walker (Walker.CreateCreature) + the given static floor bodies as one P.Scene."""
+    env = P.Environment()
+    dyn = env.dyn()
+    bodies = (floor_bodies + dyn) if floor_first else (dyn + floor_bodies)
+    return P.Scene(bodies, env.joints, iterations=50)
+
+
+def test_walker_scene_agrees_with_the_specialised_walker_kernel(gpu):
+    """The reference's default scene (CreateCreature + CreateFloor) through the GENERAL engine (scene_step_kernel) against the
+    specialised walker kernel (physics_lanes_kernel) on the same clipped actions: two independent CUDA implementations of
+    Environment.StepObjects, bit for bit on every vertex, centroid, velocity, angular velocity, angle and joint torque."""
+    n = 5
+    objs, joints = gpu.CreateCreature()
+    scene = gpu.Scene(n, objs + gpu.CreateFloor("Metal"), joints)      # constructor order: walker bodies, then the floor
+    env = gpu.EnvBatch(n, floor_materials="Metal")
+    rng = np.random.default_rng(17)
+    for step in range(12):
+        a = np.clip(rng.uniform(-1.3, 1.3, (n, 4)).astype(np.float32), -1, 1)
+        env.take_actions(a)
+        env.step_objects(gpu.DT_FRAME)
+        scene.SetTorques(a)
+        scene.StepObjects(gpu.DT_FRAME)
+        f, _ = env.get_state()      # [n, 92]: 29 vertices, 5 centroids, 5 velocities, 5 omega, 5 angles, 4 torques
+        g, col = scene.get_state()  # [n, 106]: 33 vertices, 6 centroids, 6 velocities, 6 omega, 6 angles, 4 torques
+        assert g.shape[1] == 106
+        pieces = [(f[:, 0:58], g[:, 0:58]), (f[:, 58:68], g[:, 66:76]), (f[:, 68:78], g[:, 78:88]), (f[:, 78:83], g[:, 90:95]),
+                  (f[:, 83:88], g[:, 96:101]), (f[:, 88:92], g[:, 102:106])]
+        for k, (x, y) in enumerate(pieces):
+            assert np.array_equal(bits(x), bits(y)), f"piece {k} differs at env-step {step}"
+    assert (col != 0).any()  # feet touched the floor
+
+
+def test_walker_on_rough_floor_bit_exact(gpu):
+    """Environment.CreateRoughFloor (Environment.cs:230-261; the random heights are injected) + the walker: 15 bodies, 4 joints,
+    against the NumPy restatement, for both list orders (floor last as constructed, floor first as after Walker.Reset)."""
+    P = _np_oracle()
+    heights = [int(h) for h in np.random.default_rng(5).integers(0, 100, 11)]
+    n = 2
+    for floor_first in (False, True):
+        objs, joints = gpu.CreateCreature()
+        rough = gpu.CreateRoughFloor(heights)
+        scene = gpu.Scene(n, (rough + objs) if floor_first else (objs + rough), joints)
+        m = MAT["Metal"]
+        initial_x, movement = -50, 120
+        prev = (initial_x, 800 + heights[0])
+        fb = []
+        for i in range(10):
+            x, y = initial_x + i * movement, 800 + heights[1 + i]
+            fb.append(P.hull_from_positions(m, [(x, 1050), prev, (x, y), (x + movement, 1050)], is_static=True, is_floor=True, name=f"floor{i}"))
+            prev = (x, y)
+        ref = _oracle_walker_scene(P, fb, floor_first)
+        f, col = scene.get_state()
+        rf, rcol = ref.flat_state()
+        assert np.array_equal(bits(f[0]), bits(rf)) and np.array_equal(bits(f[1]), bits(rf))
+        rng = np.random.default_rng(23)
+        for step in range(4):
+            a = np.clip(rng.uniform(-1.2, 1.2, 4).astype(np.float32), -1, 1)
+            scene.SetTorques(np.tile(a, (n, 1)))
+            ref.set_torques(list(a))
+            scene.StepObjects(gpu.DT_FRAME)
+            ref.step_objects(gpu.DT_FRAME)
+            f, col = scene.get_state()
+            rf, rcol = ref.flat_state()
+            for c in range(n):
+                assert np.array_equal(bits(f[c]), bits(rf)), f"state differs at env-step {step} (floor_first={floor_first})"
+                assert int(col[c]) == rcol
+        assert rcol != 0
