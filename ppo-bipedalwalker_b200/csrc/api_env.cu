@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "common.h"
@@ -488,13 +489,20 @@ int32_t wb_env_get_obs(wb_env_batch* env, float* obs_host) {
 
 // Pinned (page-locked) host memory is addressable from the device under unified addressing: the device-side alias of `p`, or
 // null when `p` is ordinary pageable memory
-static void* device_alias_of_pinned(const void* p) {
-  cudaPointerAttributes a{};
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+static void* device_alias_of_pinned(const void* p, size_t bytes) {
+  cudaPointerAttributes a{}, b{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeHost || !a.devicePointer) {
     cudaGetLastError();
     return nullptr;
   }
-  return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+  // the last byte must be page-locked too and alias at the same distance (one contiguous mapping, or pages pinned by wb_host_pin)
+  const char* last = static_cast<const char*>(p) + bytes - 1;
+  if (cudaPointerGetAttributes(&b, last) != cudaSuccess || b.type != cudaMemoryTypeHost ||
+      static_cast<char*>(b.devicePointer) - static_cast<char*>(a.devicePointer) != (ptrdiff_t)(bytes - 1)) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.devicePointer;
 }
 
 static int step_phases(int32_t auto_reset) {
@@ -510,10 +518,11 @@ int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_ti
   // buffers (or WB_NO_ZERO_COPY=1) take the staged path: H2D copy, launch, three D2H copies.
   static const bool zero_copy_enabled = getenv("WB_NO_ZERO_COPY") == nullptr;
   if (zero_copy_enabled) {
-    const float* a = static_cast<const float*>(device_alias_of_pinned(actions_host));
-    float* o = obs_host ? static_cast<float*>(device_alias_of_pinned(obs_host)) : env->d_obs;
-    float* r = reward_host ? static_cast<float*>(device_alias_of_pinned(reward_host)) : env->d_reward;
-    uint8_t* d = done_host ? static_cast<uint8_t*>(device_alias_of_pinned(done_host)) : env->d_done;
+    const size_t n = (size_t)env->n;
+    const float* a = static_cast<const float*>(device_alias_of_pinned(actions_host, sizeof(float) * WB_ACT * n));
+    float* o = obs_host ? static_cast<float*>(device_alias_of_pinned(obs_host, sizeof(float) * WB_OBS * n)) : env->d_obs;
+    float* r = reward_host ? static_cast<float*>(device_alias_of_pinned(reward_host, sizeof(float) * n)) : env->d_reward;
+    uint8_t* d = done_host ? static_cast<uint8_t*>(device_alias_of_pinned(done_host, n)) : env->d_done;
     if (a && o && r && d && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
       if (int32_t rc = launch(env, step_phases(auto_reset), delta_time, a, o, r, d, nullptr, nullptr, nullptr)) return rc;
       WB_CUDA(cudaStreamSynchronize(env->stream));
@@ -527,17 +536,63 @@ int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_ti
   return copy_out(env, obs_host, reward_host, done_host);
 }
 
+// Small managed arrays (the reference's 12-float observation, 4-float action ...) usually SHARE a page, and cudaHostRegister
+// refuses a range that touches an already registered page.  wb_host_pin therefore registers the page-rounded range in one call
+// and, if that is refused, page by page, skipping the pages some earlier call registered; what THIS call registered is
+// remembered per caller pointer so that wb_host_unpin releases exactly that.
+static std::mutex g_pin_mutex;
+static std::unordered_map<void*, std::vector<void*>> g_pins;   // caller pointer -> base addresses this call registered
+constexpr uintptr_t kHostPage = 4096;
+
 int32_t wb_host_pin(void* host_ptr, size_t bytes) {
   WB_REQUIRE(host_ptr && bytes > 0, "bad argument");
   if (int32_t rc = require_device()) return rc;
-  WB_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault));
+  const uintptr_t first = reinterpret_cast<uintptr_t>(host_ptr) & ~(kHostPage - 1);
+  const uintptr_t last = (reinterpret_cast<uintptr_t>(host_ptr) + bytes + kHostPage - 1) & ~(kHostPage - 1);
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
+  WB_REQUIRE(g_pins.find(host_ptr) == g_pins.end(), "wb_host_pin: this buffer is already pinned");
+  std::vector<void*> mine;
+  cudaError_t e = cudaHostRegister(reinterpret_cast<void*>(first), last - first, cudaHostRegisterDefault);
+  if (e == cudaSuccess) {
+    mine.push_back(reinterpret_cast<void*>(first));
+  } else if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    for (uintptr_t page = first; page < last; page += kHostPage) {
+      e = cudaHostRegister(reinterpret_cast<void*>(page), kHostPage, cudaHostRegisterDefault);
+      if (e == cudaSuccess) {
+        mine.push_back(reinterpret_cast<void*>(page));
+      } else if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();  // an earlier wb_host_pin (or the caller) page-locked it: nothing to do
+      } else {
+        cudaGetLastError();
+        for (void* q : mine) cudaHostUnregister(q);
+        return fail(WB_ERR_CUDA, "wb_host_pin: cudaHostRegister: %s", cudaGetErrorString(e));
+      }
+    }
+  } else {
+    cudaGetLastError();
+    return fail(WB_ERR_CUDA, "wb_host_pin: cudaHostRegister: %s", cudaGetErrorString(e));
+  }
+  g_pins.emplace(host_ptr, std::move(mine));
   return WB_OK;
 }
 
 int32_t wb_host_unpin(void* host_ptr) {
   WB_REQUIRE(host_ptr, "null argument");
   if (int32_t rc = require_device()) return rc;
-  WB_CUDA(cudaHostUnregister(host_ptr));
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
+  auto it = g_pins.find(host_ptr);
+  WB_REQUIRE(it != g_pins.end(), "wb_host_unpin: this buffer was not pinned with wb_host_pin");
+  cudaError_t first_error = cudaSuccess;
+  for (void* q : it->second) {
+    const cudaError_t e = cudaHostUnregister(q);
+    if (e != cudaSuccess && first_error == cudaSuccess) first_error = e;
+  }
+  g_pins.erase(it);
+  if (first_error != cudaSuccess) {
+    cudaGetLastError();
+    return fail(WB_ERR_CUDA, "wb_host_unpin: cudaHostUnregister: %s", cudaGetErrorString(first_error));
+  }
   return WB_OK;
 }
 

@@ -175,34 +175,51 @@ def test_pinned_host_buffers_zero_copy_path_matches_oracle(gpu, O):
 
 def test_host_pin_makes_numpy_buffers_zero_copy(gpu, O):
     """wb_host_pin / wb_host_unpin (what the C# shim does with its GCHandle-pinned arrays): registered numpy buffers take the
-    zero-copy path of wb_env_step and give the oracle's bits."""
-    n = 64
-    env = gpu.EnvBatch(n)
-    ref = O.EnvBatch(n)
-    # page-aligned so that registering one buffer never overlaps another one's pages
-    def aligned(shape, dtype):
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        raw = np.empty(nbytes + 8192, np.uint8)
-        off = (-raw.ctypes.data) % 4096
-        return raw[off:off + ((nbytes + 4095) // 4096) * 4096][:nbytes].view(dtype).reshape(shape), raw
-    a, _ka = aligned((n, 4), np.float32)
-    obs, _ko = aligned((n, 12), np.float32)
-    rew, _kr = aligned((n,), np.float32)
-    done, _kd = aligned((n,), np.uint8)
-    bufs = [a, obs, rew, done]
-    for b in bufs:
-        gpu.pin_host(b)
-    try:
-        rng = np.random.default_rng(3)
-        for t in range(10):
-            a[:] = rng.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
-            env.step(a, out=(obs, rew, done))
-            robs, rrew, rdone = ref.step(a.copy())
-            assert np.array_equal(bits(obs), bits(robs)) and np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone), f"step {t}"
-    finally:
+    zero-copy path of wb_env_step and give the oracle's bits -- page-aligned buffers, and the realistic case of four small
+    arrays that SHARE one page (cudaHostRegister refuses overlapping pages: wb_host_pin registers what is still missing)."""
+    for shared_page in (False, True):
+        n = 3 if shared_page else 64
+        env = gpu.EnvBatch(n)
+        ref = O.EnvBatch(n)
+        if shared_page:
+            raw = np.zeros(8192, np.uint8)
+            off = (-raw.ctypes.data) % 4096 + 64      # all four arrays inside one page, 16-byte aligned
+            def carve(nbytes, dtype, shape):
+                nonlocal off
+                v = raw[off:off + nbytes].view(dtype).reshape(shape)
+                off += (nbytes + 15) // 16 * 16
+                return v
+            a, obs = carve(n * 16, np.float32, (n, 4)), carve(n * 48, np.float32, (n, 12))
+            rew, done = carve(n * 4, np.float32, (n,)), carve(n, np.uint8, (n,))
+            keep = [raw]
+        else:
+            def aligned(shape, dtype):
+                nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                r = np.empty(nbytes + 8192, np.uint8)
+                o = (-r.ctypes.data) % 4096
+                return r[o:o + nbytes].view(dtype).reshape(shape), r
+            (a, k0), (obs, k1), (rew, k2), (done, k3) = (aligned((n, 4), np.float32), aligned((n, 12), np.float32),
+                                                          aligned((n,), np.float32), aligned((n,), np.uint8))
+            keep = [k0, k1, k2, k3]
+        bufs = [a, obs, rew, done]
         for b in bufs:
-            gpu.unpin_host(b)
-    assert_state_equal(env, ref, "host_pin path")
+            gpu.pin_host(b)
+        with pytest.raises(gpu.WalkerB200Error):
+            gpu.pin_host(a)                           # the same buffer twice is an error, not a silent double registration
+        try:
+            rng = np.random.default_rng(3)
+            for t in range(10):
+                a[:] = rng.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+                env.step(a, out=(obs, rew, done))
+                robs, rrew, rdone = ref.step(a.copy())
+                assert np.array_equal(bits(obs), bits(robs)) and np.array_equal(bits(rew), bits(rrew)) and np.array_equal(done, rdone), f"step {t}"
+        finally:
+            for b in bufs:
+                gpu.unpin_host(b)
+        with pytest.raises(gpu.WalkerB200Error):
+            gpu.unpin_host(a)
+        assert_state_equal(env, ref, f"host_pin path (shared_page={shared_page})")
+        del keep
 
 
 def test_committed_golden_rollout(gpu):
