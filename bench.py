@@ -336,7 +336,37 @@ def run_ours(args):
                              "frac": na * BYTES_PER_ENV_STEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
                              "substep_granular_frac": na * 50 * BYTES_PER_SUBSTEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
                              "traffic": ncu_traffic("physics_lanes_kernel_262144")}}
+    # ---- Iterations = 1 (SURVEY 8d asks for it): ONE substep per launch from the same mixed state, so the 376-byte record really
+    #      crosses HBM twice per substep -- the measured counterpart of the "substep-granular" accounting above
+    hp1 = wb.default_hyperparams()
+    hp1.iterations = 1
+    env4 = wb.EnvBatch(na, floor_materials="Wood", hp=hp1, stream=stream)
+    env4.set_state(*env3.get_state())
     del env3
+    for w in range(3):
+        env4.step_dev(acts3[w % 8], obs3, rew3, done3)
+    barrier()
+    tot4 = 0.0
+    for k in range(ka):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env4.step_dev(acts3[k % 8], obs3, rew3, done3)
+        e1.record()
+        e1.synchronize()
+        tot4 += e0.elapsed_time(e1)
+    barrier()
+    t4 = torch.tensor([tot4], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+    ms4 = float(t4.item()) / ka
+    at_scale["iterations_1"] = {
+        "value": world * na / (ms4 * 1e-3), "unit": "substeps/s (Hyperparameters.Iterations = 1: one substep per env-step and per launch)",
+        "ms_per_step": ms4, "steps": ka, "lanes_per_walker": env4.get_variant(),
+        "roofline": {"bound": "hbm", "achieved": na * BYTES_PER_ENV_STEP / (ms4 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": na * BYTES_PER_ENV_STEP / (ms4 * 1e-3) / 1e9 / hbm_peak,
+                     "note": "824 B per walker per launch (state in + out, actions, obs/reward/done)"}}
+    del env4
 
     if rank == 0:
         hbm, tflops, which = measured_peaks()

@@ -177,6 +177,7 @@ struct wb_env_batch {
   float* d_pos = nullptr;      // [2][n_pad]
   uint8_t* d_floor_mat = nullptr;
   uint8_t* d_walker_mat = nullptr;
+  uint32_t* d_axis_cache = nullptr;  // [n_pad] separating-axis hints of the compacting kernel, carried across launches
   // device I/O staging for the host-pointer entry points
   float* d_actions = nullptr;  // [n][4]
   float* d_obs = nullptr;      // [n][12]
@@ -251,6 +252,7 @@ static int32_t launch(wb_env_batch* env, int phases, float dt, const float* d_ac
   p.pos = env->d_pos;
   p.floor_mat = env->d_floor_mat;
   p.walker_mat = env->d_walker_mat;
+  p.axis_cache = env->d_axis_cache;
   p.actions = d_actions;
   p.reset_mask = d_mask;
   p.obs = d_obs;
@@ -312,6 +314,8 @@ int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const u
   WB_CUDA(cudaMalloc(&env->d_pos, sizeof(float) * 2 * np));
   WB_CUDA(cudaMalloc(&env->d_floor_mat, np));
   WB_CUDA(cudaMalloc(&env->d_walker_mat, np));
+  WB_CUDA(cudaMalloc(&env->d_axis_cache, sizeof(uint32_t) * np));
+  WB_CUDA(cudaMemset(env->d_axis_cache, 0, sizeof(uint32_t) * np));
   WB_CUDA(cudaMalloc(&env->d_actions, sizeof(float) * WB_ACT * np));
   WB_CUDA(cudaMalloc(&env->d_obs, sizeof(float) * WB_OBS * np));
   WB_CUDA(cudaMalloc(&env->d_reward, sizeof(float) * np));
@@ -341,6 +345,7 @@ int32_t wb_env_destroy(wb_env_batch* env) {
   cudaFree(env->d_pos);
   cudaFree(env->d_floor_mat);
   cudaFree(env->d_walker_mat);
+  cudaFree(env->d_axis_cache);
   cudaFree(env->d_actions);
   cudaFree(env->d_obs);
   cudaFree(env->d_reward);

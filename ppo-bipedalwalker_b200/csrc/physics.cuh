@@ -33,6 +33,8 @@ struct PhysicsParams {
   float* pos;          // [2][n_pad]  Walker._position (Walker.cs:19)
   const uint8_t* floor_mat;   // [n_pad]
   const uint8_t* walker_mat;  // [n_pad]
+  uint32_t* axis_cache;       // [n_pad] or null: the compacting kernel's last separating axis per ordered leg pair (4 x 8 bits),
+                              // carried from launch to launch (a hint only: any value 0..11 is a legal first axis to test)
   const float* actions;       // [n][4]
   const uint8_t* reset_mask;  // [n] or null
   float* obs;          // [n][12]

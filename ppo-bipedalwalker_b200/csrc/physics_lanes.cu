@@ -1160,16 +1160,30 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
 
   for (int w = tid; w < (int)(sizeof(FloorConst) / 4); w += kE)
     reinterpret_cast<uint32_t*>(&S.floor)[w] = reinterpret_cast<const uint32_t*>(&c_floor)[w];
-  // stage the record of my walker (SoA rows are contiguous over walkers: coalesced)
-#pragma unroll 8
-  for (int f = 0; f < 88; f++)
-    S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = live ? p.state[(size_t)f * p.n_pad + env] : c_init_state[f];
+  // stage the record of my walker (SoA rows are contiguous over walkers: coalesced); 22 independent loads in flight per thread
+#pragma unroll 1
+  for (int f0 = 0; f0 < 88; f0 += 22) {
+    float r[22];
+#pragma unroll
+    for (int j = 0; j < 22; j++) r[j] = p.state[(size_t)(f0 + j) * p.n_pad + envc];
+#pragma unroll
+    for (int j = 0; j < 22; j++) {
+      const int f = f0 + j;
+      S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = live ? r[j] : c_init_state[f];
+    }
+  }
   for (int w = tid; w < (int)(sizeof(Material) * WB_MAX_MATERIALS / 4); w += kE)
     reinterpret_cast<uint32_t*>(S.mtab)[w] = reinterpret_cast<const uint32_t*>(c_materials)[w];
   S.wmat[tid] = p.walker_mat[envc];
   S.fmat[tid] = p.floor_mat[envc];
+  {
+    const uint32_t packed = (p.axis_cache != nullptr && live) ? p.axis_cache[env] : 0u;
 #pragma unroll
-  for (int s = 0; s < 4; s++) S.axis[s * kE + tid] = 0;
+    for (int s = 0; s < 4; s++) {
+      const uint32_t a = (packed >> (8 * s)) & 0xFFu;
+      S.axis[s * kE + tid] = (unsigned char)(a < 12u ? a : 0u);
+    }
+  }
   if (tid == 0) S.count[0] = S.count[1] = 0;
   scope_sync<kE>();  // the floor constants / counters written above are read by every thread of the scope
   EV e;
@@ -1320,6 +1334,9 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
     p.steps[env] = steps;
     p.pos[env] = pos.x;
     p.pos[p.n_pad + env] = pos.y;
+    if (p.axis_cache != nullptr)
+      p.axis_cache[env] = (uint32_t)S.axis[tid] | ((uint32_t)S.axis[kE + tid] << 8) | ((uint32_t)S.axis[2 * kE + tid] << 16) |
+                          ((uint32_t)S.axis[3 * kE + tid] << 24);
 #pragma unroll 8
     for (int f = 0; f < 88; f++) p.state[(size_t)f * p.n_pad + env] = S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)];
   }

@@ -2,7 +2,7 @@
 for every variant restore the snapshot, time K fused env-steps (CUDA events on the launching stream) and hash the final
 state: all variants must end bit-identical (printed as `same=True`).
 
-usage: python scripts/sweep_physics.py N K WARM variant [variant ...]
+usage: [WB_ITERATIONS=k] python scripts/sweep_physics.py N K WARM variant [variant ...]
 """
 import hashlib
 import os
@@ -19,7 +19,9 @@ warm = int(sys.argv[3])
 variants = [int(v) for v in sys.argv[4:]]
 wb = ge.load_package()
 wb.init(0)
-env = wb.EnvBatch(n, floor_materials="Wood")
+hp = wb.default_hyperparams()
+hp.iterations = int(os.environ.get("WB_ITERATIONS", hp.iterations))  # Hyperparameters.Iterations (substeps per env-step)
+env = wb.EnvBatch(n, floor_materials="Wood", hp=hp)
 rng = np.random.default_rng(0)
 acts = [torch.from_numpy(rng.uniform(-1, 1, (n, 4)).astype(np.float32)).cuda() for _ in range(8)]
 obs = torch.empty(n, 12, device="cuda")
