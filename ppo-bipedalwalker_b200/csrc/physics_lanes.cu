@@ -943,7 +943,7 @@ static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t str
 // One thread per environment (as L = 1 above), but a warp of the plain kernel executes the UNION of its 32 walkers' branches,
 // and in a decorrelated rollout the expensive branches are rare per walker yet almost always present in some lane: a leg
 // pair's AABBs overlap 85 % of the time but SAT finds a collision in only ~10 % of the substeps, the floor is touched in ~5 %,
-// a joint needs correcting in ~20 % (profiles/physics_r1_hotspots.md: 31 % of the executed lane-slots did useful work).
+// a joint needs correcting in ~20 % (profiles/hotspots_r1.md, r1d: 31 % of the executed lane-slots did useful work).
 // Here a CTA of kE walkers (256 by default) advances in lockstep PHASES, and each phase has two stages:
 //   stage 1  every thread, for ITS walker: the cheap, common part -- integrate the body; for a leg pair test the separating
 //            axis that separated this pair last time (temporal coherence; any order of the axis tests gives the reference's
@@ -952,7 +952,8 @@ static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t str
 //            push an item (walker, body / joint) onto a queue in shared memory.
 //   stage 2  after a CTA barrier, the queued items are processed DENSELY: thread t takes item t (any thread can work on any
 //            walker: the state columns live in shared memory), runs the full resolve_pair / joint_step of the plain kernel
-//            on that walker's columns and records the separating axis it found, if any, for the next substep.
+//            on that walker's columns and records the separating axis it found, if any, for the next substep (the hints
+//            also survive from launch to launch: PhysicsParams::axis_cache).
 // Left and right leg are swept in the same phase (they share no mutable state, see the leg split above), which halves the
 // number of barriers and doubles the queue density.  Arithmetic and order per walker are those of the plain kernel: the
 // results are bit-identical (tests/test_physics_gpu.py runs every variant against the oracle).
@@ -961,8 +962,10 @@ using namespace pl;
 
 // kE walkers (= threads) share one queue and advance in lockstep.  Measured at 262144 walkers (ms per env-step): kE = 32 (ONE
 // WARP per CTA, rounds separated by __syncwarp only, no block barrier anywhere) 8.86 -- sparse per-warp queues execute the
-// expensive stage once per warp however few items it has; 64: 7.35; 128: 5.93; 256: 5.45 (default); 512: 6.06 (one CTA per SM:
-// nothing overlaps its barriers).  Aggregation beats barrier cost up to the point where CTAs stop overlapping each other.
+// expensive stage once per warp however few items it has; 64: 7.35; 128: 5.93; 256: 5.45 (default; 4.79 today); 512: 6.06 (one CTA
+// per SM: nothing overlaps its barriers); 192 walkers x 3 CTAs per SM needs <= 96 registers per thread: 6.3.  Aggregation beats
+// barrier cost up to the point where CTAs stop overlapping each other.  Shared memory (360 B per walker) and registers both cap
+// residency at 512 walkers per SM.
 template <int kE>
 struct Shared {
   float state[(kV2Count * 2 + kFCount) * kE];
