@@ -140,3 +140,34 @@ def test_reference_scene_pieces_match_the_numpy_restatement(wb, O):
             raise AssertionError("accepted an invalid rough floor")
         except ValueError:
             pass
+
+
+def test_refharness_glue_exports_and_compares_the_golden_rollout(tmp_path):
+    """scripts/refharness_io.py: the input file for the C# RefHarness is well formed, and the comparer accepts exactly the golden
+    states (and names the first differing field otherwise).  The harness itself needs a .NET SDK and is not run here."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "scripts", "refharness_io.py")
+    inp = tmp_path / "golden_actions.txt"
+    subprocess.run([sys.executable, script, "export", str(inp)], check=True, capture_output=True)
+    lines = inp.read_text().splitlines()
+    assert lines[0] == "8 90 50" and lines[1].split() == ["Ice", "Wood", "Paper", "Titanium", "Carpet", "Rubber", "Metal", "SuperRubber"]
+    assert len(lines) == 2 + 90 * 8 and all(len(ln.split()) == 5 for ln in lines[2:])
+    g = np.load(os.path.join(root, "tests", "golden", "physics_rollout.npz"))
+    words = np.ascontiguousarray(g["states"], np.float32).view(np.uint32)
+
+    def dump(a, path):
+        with open(path, "w") as fh:
+            for t in range(a.shape[0]):
+                for e in range(a.shape[1]):
+                    fh.write(" ".join(f"{x:08x}" for x in a[t, e]) + "\n")
+
+    dump(words, tmp_path / "ok.txt")
+    bad = words.copy()
+    bad[10, 3, 70] ^= 1
+    dump(bad, tmp_path / "bad.txt")
+    ok = subprocess.run([sys.executable, script, "compare", str(tmp_path / "ok.txt")], capture_output=True, text=True)
+    assert ok.returncode == 0 and "pinned" in ok.stdout
+    res = subprocess.run([sys.executable, script, "compare", str(tmp_path / "bad.txt")], capture_output=True, text=True)
+    assert res.returncode == 1 and "env-step 10, walker 3" in res.stdout and "LLU.velocity.x" in res.stdout
