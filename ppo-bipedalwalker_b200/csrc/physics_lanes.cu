@@ -973,7 +973,7 @@ struct Shared {
   unsigned char wmat[kE], fmat[kE];     // walker / floor material id per walker
   FloorConst floor;
   unsigned char axis[4 * kE];   // last separating axis per ordered leg pair {LLL->LLU, LLU->LLL, RLL->RLU, RLU->RLL}
-  unsigned short queue[2 * kE];
+  unsigned short queue[3 * kE];  // a floor round holds at most three items per walker (two leg segments + the Body)
   int count[2];  // ping-pong: the counter of the next round is cleared while the current one drains
 };
 // The noinline stages below rebuild their shared-memory pointers from this array instead of receiving pointers as arguments:
@@ -1263,26 +1263,29 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
       round([&] { drain<kItemJoint, kE>(parity); });
       push(S, parity, joint_gap_active(3), tid | (3 << 10));
       round([&] { drain<kItemJoint, kE>(parity); });
-      // ---- body sweep: {LLL, RLL}, {LLU, RLU}, {Body}; per body [floor if floor-first] [leg partner] [floor if floor-last]
+      // ---- body sweep: {LLL, RLL, Body}, then {LLU, RLU}; per leg segment [floor if floor-first] [leg partner] [floor if
+      //      floor-last].  The Body only ever meets the floor (Walker.cs:204-209), so its step is independent of both legs during
+      //      the sweep: it is integrated with the first pair and its floor item rides in that pair's first floor round instead
+      //      of costing a round of its own.
 #pragma unroll 1
-      for (int ph = 0; ph < 3; ph++) {
-        const int b0 = ph == 0 ? LLL : ph == 1 ? LLU : BODY;
+      for (int ph = 0; ph < 2; ph++) {
+        const int b0 = ph == 0 ? LLL : LLU;
         const int b1 = ph == 0 ? RLL : RLU;
-        const int nb = ph == 2 ? 1 : 2;
         integrate_body<kE>(tid, b0, dt);
-        if (nb == 2) integrate_body<kE>(tid, b1, dt);
-        if (ph == 2) {
-          const bool fb = floor_pair_needs_work<kE>(tid, BODY);
-          if (fb) e.flags |= 1 << BODY;
-          push(S, parity, fb, tid | (BODY << 10));
-          round([&] { drain<kItemFloor, kE>(parity); });
-          continue;
-        }
+        integrate_body<kE>(tid, b1, dt);
+        bool body_pending = ph == 0;
+        if (body_pending) integrate_body<kE>(tid, BODY, dt);
         if (any_first) {
           const bool f0 = floor_first && floor_pair_needs_work<kE>(tid, b0), f1 = floor_first && floor_pair_needs_work<kE>(tid, b1);
           e.flags |= (f0 ? 1 << b0 : 0) | (f1 ? 1 << b1 : 0);
           push(S, parity, f0, tid | (b0 << 10));
           push(S, parity, f1, tid | (b1 << 10));
+          if (body_pending) {
+            const bool fb = floor_pair_needs_work<kE>(tid, BODY);
+            if (fb) e.flags |= 1 << BODY;
+            push(S, parity, fb, tid | (BODY << 10));
+            body_pending = false;
+          }
           round([&] { drain<kItemFloor, kE>(parity); });
         }
         push(S, parity, pole_pair_needs_work<kE>(tid, b0, partner_of(b0)), tid | (b0 << 10));
@@ -1293,6 +1296,12 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
           e.flags |= (f0 ? 1 << b0 : 0) | (f1 ? 1 << b1 : 0);
           push(S, parity, f0, tid | (b0 << 10));
           push(S, parity, f1, tid | (b1 << 10));
+          if (body_pending) {  // (a CTA whose walkers are all floor-last)
+            const bool fb = floor_pair_needs_work<kE>(tid, BODY);
+            if (fb) e.flags |= 1 << BODY;
+            push(S, parity, fb, tid | (BODY << 10));
+            body_pending = false;
+          }
           round([&] { drain<kItemFloor, kE>(parity); });
         }
       }
