@@ -336,7 +336,29 @@ def run_ours(args):
                              "frac": na * BYTES_PER_ENV_STEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
                              "substep_granular_frac": na * 50 * BYTES_PER_SUBSTEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
                              "traffic": ncu_traffic("physics_lanes_kernel_262144")}}
-    # ---- Iterations = 1 (SURVEY 8d asks for it): ONE substep per launch from the same mixed state, so the 376-byte record really
+    # ---- the same after 448 more env-steps: by then (almost) every walker has been through its first reset, the floor is first
+    #      in every list (Walker.cs:212-223) and no CTA of the compacting kernel needs the floor-last rounds any more
+    for w in range(448):
+        env3.step_dev(acts3[w % 8], obs3, rew3, done3)
+    barrier()
+    tot3b = 0.0
+    for k in range(ka):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env3.step_dev(acts3[k % 8], obs3, rew3, done3)
+        e1.record()
+        e1.synchronize()
+        tot3b += e0.elapsed_time(e1)
+    barrier()
+    t3b = torch.tensor([tot3b], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t3b, op=dist.ReduceOp.MAX)
+    ms3b = float(t3b.item()) / ka
+    at_scale["after_512_env_steps"] = {"value": world * na / (ms3b * 1e-3), "unit": "env-steps/s", "ms_per_step": ms3b, "steps": ka,
+                                       "note": "same batch 448 env-steps later: every list is floor-first (steady state of a long rollout)"}
+
+    # ---- Iterations = 1 (SURVEY 8d asks for it): ONE substep per launch from the state of the same batch, so the 376-byte record really
     #      crosses HBM twice per substep -- the measured counterpart of the "substep-granular" accounting above
     hp1 = wb.default_hyperparams()
     hp1.iterations = 1
