@@ -9,8 +9,11 @@ env-step (seeded, generated once), dt = 0x1.111134p-6, Iterations = 50, auto-res
 env-step kernel over all walkers of the rank.  Multi-GPU: environments are block-sharded, no data-path collective
 (weak scaling, 4096 walkers per GPU).
 
-Both arms first run PREROLL (64) untimed env-steps so that the walkers are in a mixed, decorrelated state (right after
-construction all walkers are identical, which flatters a SIMT kernel: no divergence).
+Both arms first run PREROLL (512) untimed env-steps so that the batch is in the state a long rollout is in: decorrelated (right
+after construction all walkers are identical, which flatters a SIMT kernel: no divergence) and past every walker's first reset
+(the reference's body list changes order exactly once, at the first Walker.Reset -- Walker.cs:212-223 -- and while a batch still
+holds both orders the kernels run extra floor phases: 4096 walkers take 0.404 ms per env-step 68 steps in, 0.376 ms 512 steps
+in, 0.370 ms 900 steps in; SURVEY 8d's plan for this config is likewise "timed after 100 warm-up", 1000 steps).
 
 Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps an L2 flush (256 MiB
 memset) runs OUTSIDE the event pairs; ms_per_step = sum of the K event intervals / K, max over ranks.
@@ -38,7 +41,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 N_ENVS_PER_GPU = 4096
 N_ENVS_AT_SCALE = 262144   # "at_scale": the same step with the GPU full (one lane per walker)
-PREROLL = 64               # untimed env-steps before the warm-up: the batch leaves the synchronized spawn transient
+PREROLL = 512              # untimed env-steps before the warm-up: see the module docstring
 SEED = 1234
 BYTES_PER_ENV_STEP = 2 * 376 + 16 + 56   # read state + actions, write state + obs/reward/done = 824 B
 BYTES_PER_SUBSTEP = 2 * 376              # if the state round-tripped HBM every substep (it does not: 50 substeps are fused)
@@ -336,28 +339,6 @@ def run_ours(args):
                              "frac": na * BYTES_PER_ENV_STEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
                              "substep_granular_frac": na * 50 * BYTES_PER_SUBSTEP / (ms3 * 1e-3) / 1e9 / hbm_peak,
                              "traffic": ncu_traffic("physics_lanes_kernel_262144")}}
-    # ---- the same after 448 more env-steps: by then (almost) every walker has been through its first reset, the floor is first
-    #      in every list (Walker.cs:212-223) and no CTA of the compacting kernel needs the floor-last rounds any more
-    for w in range(448):
-        env3.step_dev(acts3[w % 8], obs3, rew3, done3)
-    barrier()
-    tot3b = 0.0
-    for k in range(ka):
-        flush()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        env3.step_dev(acts3[k % 8], obs3, rew3, done3)
-        e1.record()
-        e1.synchronize()
-        tot3b += e0.elapsed_time(e1)
-    barrier()
-    t3b = torch.tensor([tot3b], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t3b, op=dist.ReduceOp.MAX)
-    ms3b = float(t3b.item()) / ka
-    at_scale["after_512_env_steps"] = {"value": world * na / (ms3b * 1e-3), "unit": "env-steps/s", "ms_per_step": ms3b, "steps": ka,
-                                       "note": "same batch 448 env-steps later: every list is floor-first (steady state of a long rollout)"}
-
     # ---- Iterations = 1 (SURVEY 8d asks for it): ONE substep per launch from the state of the same batch, so the 376-byte record really
     #      crosses HBM twice per substep -- the measured counterpart of the "substep-granular" accounting above
     hp1 = wb.default_hyperparams()
