@@ -155,8 +155,7 @@ using namespace wb;
 static int default_lanes(int n_envs, int sm_count) {
   const long per_sm = ((long)n_envs + sm_count - 1) / sm_count;
   if (per_sm <= 10) return 32;  // a handful of walkers (the reference's single-walker case): all 32 lanes on one walker
-  if (per_sm <= 18) return 16;
-  if (per_sm <= 40) return 8;
+  if (per_sm <= 48) return 8;
   if (per_sm <= 160) return 4;
   if (per_sm <= 200) return 2;
   return 1001;  // GPU full: one thread per walker with CTA-level work compaction
