@@ -113,8 +113,18 @@ def make_actions(n, steps, rank):
     return rng.uniform(-1.0, 1.0, (steps, n, 4)).astype(np.float32)
 
 
+def host_threads():
+    """All host threads this process may use.  Passed to the oracle EXPLICITLY: torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would silently turn the "all host threads" CPU arm into a single-threaded one."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(O, budget_s=12.0, max_steps=4000, nthreads=0):
     """The oracle port on the host cores: the same workload, a bounded sample (~budget_s of CPU work)."""
+    nthreads = nthreads if nthreads > 0 else host_threads()
     n = N_ENVS_PER_GPU
     env = O.EnvBatch(n, floor="Wood")
     acts = make_actions(n, 8, 0)
@@ -141,14 +151,14 @@ def run_reference(args):
     n = N_ENVS_PER_GPU
     env = O.EnvBatch(n, floor="Wood")
     acts = make_actions(n, PREROLL + args.warmup + args.steps, 0)
+    cores = host_threads()
     for w in range(PREROLL + args.warmup):
-        env.step(acts[w])
+        env.step(acts[w], nthreads=cores)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        env.step(acts[PREROLL + args.warmup + k])
+        env.step(acts[PREROLL + args.warmup + k], nthreads=cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": "walker env-steps/sec (SAT physics step)", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,

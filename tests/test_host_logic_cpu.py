@@ -40,10 +40,13 @@ def test_shard_range_partitions_exactly():
 
 
 def test_bench_reference_arm_runs_on_cpu():
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the arm must still use all host threads (it passes the count explicitly)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["config"]["walkers_per_gpu"] == 4096 and line["higher_is_better"] is True
