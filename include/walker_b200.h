@@ -165,7 +165,7 @@ int32_t wb_debug_rcp_sqrt_check(uint32_t first_bits, uint64_t count, uint64_t* m
 
 /* ---- general scenes: the IObject plugin surface (Objects/IObject.cs:7-10) ----
  * N lockstep copies of an arbitrary list of convex polygons (Square / Triangle / Hexagon / Pole / Hull ..., 3..16 vertices,
- * Objects/RigidBodies/*.cs) with any IMaterial, static / floor flags, association ("no collide") lists (RigidBody.cs:143-152) and
+ * Objects/RigidBodies/{Square,Triangle,Hexagon,Pole,Hull}.cs) with any IMaterial, static / floor flags, association ("no collide") lists (RigidBody.cs:143-152) and
  * joints (Joint.cs), stepped by Environment.StepObjects (Environment.cs:126-143).  List order = index order.  The walker-specialised
  * wb_env_* path covers the reference's default scene much faster; this path covers everything else the engine can be asked to do. */
 typedef struct wb_scene wb_scene;

@@ -74,3 +74,30 @@ def test_material_registry_is_host_side(wb):
     assert (im.value, round(e.value, 6), round(mu.value, 6)) == (3.0, 0.4, 0.6)
     assert wb.lib().wb_material_get(1, C.byref(im), C.byref(e), C.byref(mu)) == 0 and im.value == 20.0  # Wood
     assert wb.lib().wb_material_get(63, C.byref(im), C.byref(e), C.byref(mu)) != 0
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "ppo-bipedalwalker_b200", "lib")
+    exe = str(tmp_path / "c_abi_smoke")
+    cc = shutil.which("gcc") or shutil.which("cc")
+    cmd = [cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+           os.path.join(root, "examples", "c_abi_smoke.c"), "-o", exe, "-L", libdir, "-lwalker_b200", f"-Wl,-rpath,{libdir}"]
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_header_is_plain_c99_and_a_c_program_links_and_is_refused_without_a_gpu(wb, tmp_path):
+    """include/walker_b200.h compiles as strict C99 (-Wall -Wextra -Werror -pedantic) and examples/c_abi_smoke.c links against the
+    library with no CUDA or C++ on its side; without an sm_100 device the program is refused loudly (exit 3: WB_ERR_NO_DEVICE)."""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present (tests/test_physics_gpu.py runs the program)")
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 3 and "no CPU fallback" in res.stderr

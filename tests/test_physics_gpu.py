@@ -1,5 +1,7 @@
 """GPU parity tests proper: the CUDA physics path, called through the C ABI, against the CPU oracle on the
 same seeded inputs.  Bar: contact pairs / axis indices / contact points / state all BIT-EXACT."""
+import os
+
 import numpy as np
 import pytest
 
@@ -220,6 +222,18 @@ def test_host_pin_makes_numpy_buffers_zero_copy(gpu, O):
             gpu.unpin_host(a)
         assert_state_equal(env, ref, f"host_pin path (shared_page={shared_page})")
         del keep
+
+
+def test_plain_c_program_drives_the_abi(gpu, tmp_path):
+    """examples/c_abi_smoke.c (C99, no CUDA headers): wb_env_step with malloc'ed buffers and with wb_host_pin'ed buffers agree."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi_cpu import _build_c_example
+    exe = _build_c_example(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "staged and zero-copy paths agree" in res.stdout
 
 
 def test_committed_golden_rollout(gpu):
