@@ -45,6 +45,7 @@ extern "C" {
 #define WB_ERR_NO_DEVICE 2  /* no CUDA device / wrong architecture            */
 #define WB_ERR_CUDA 3       /* CUDA runtime error (message in wb_last_error)  */
 #define WB_ERR_UNSUPPORTED 4
+#define WB_ERR_COMM 5       /* a data-parallel gradient exchange timed out    */
 
 #define WB_STATE_FLOATS 92
 #define WB_STATE_INTS 2
@@ -238,9 +239,21 @@ int32_t wb_policy_sample_philox_dev(wb_policy* p, int32_t n, const float* states
 int32_t wb_policy_act_dev(wb_policy* p, int32_t n, const float* states_dev, uint64_t seed, uint64_t step, float* actions_dev,
                           float* logp_dev, float* mean_dev, float* value_dev);
 /* rollout -> update glue for N lockstep environments (PPOAgent.cs:414-498 applied per episode fragment): time-major buffers
- * [horizon][n_envs]; done != 0 marks the last step of an episode; the segment end truncates like a trajectory end */
+ * [horizon][n_envs]; done != 0 marks the last step of an episode (the recurrences restart there like at a trajectory end).
+ * Segment end: last_values_dev [n_envs] = the critic's estimate of the observation AFTER the last step; an episode still
+ * running at the segment end continues the recurrence from it (next return = next value = V(s_T)).  This is a DEVIATION the
+ * lockstep form needs -- the reference only ever trains on complete episodes (PPOAgent.cs:147) -- and is skipped where
+ * dones[horizon-1] is set.  last_values_dev == NULL truncates instead (the segment end is scored like a trajectory end).
+ * With hp.normalize_advantages the whole [horizon x n_envs] pool is normalised (wb_normalize_advantages_dev, stage -1). */
 int32_t wb_segment_returns_dev(wb_policy* p, int32_t n_envs, int32_t horizon, const float* rewards_dev, const float* values_dev,
-                               const uint8_t* dones_dev, float* returns_dev, float* advantages_dev);
+                               const uint8_t* dones_dev, const float* last_values_dev, float* returns_dev, float* advantages_dev);
+/* PPOAgent.Normalize (PPOAgent.cs:461-472) over a pool of advantages: mean = (float)(sum / count) and
+ * std = (float)sqrt(sum (x - mean)^2 / count) accumulated in double, x = (x - mean) / (std + hp.epsilon) (the reference
+ * uses the PPO clip epsilon here).  stage -1 runs everything for a single process.  A data-parallel caller runs stage 0,
+ * all-reduces (sum) the stats buffer, runs stage 1, all-reduces it again, runs stage 2; n_global = pool size over all ranks. */
+int32_t wb_normalize_advantages_dev(wb_policy* p, int32_t stage, int64_t n_local, int64_t n_global, float* advantages_dev);
+/* device address + length (in doubles) of the partial-sum buffer the stages above exchange through */
+int32_t wb_normalize_stats_buffer(wb_policy* p, void** dev_ptr_out, int32_t* n_doubles_out);
 /* PPOAgent.CreateBatches (PPOAgent.cs:501-540): gather rows index_dev[0..batch) of the rollout pool into a contiguous minibatch */
 int32_t wb_gather_minibatch_dev(wb_policy* p, int32_t batch, const int32_t* index_dev, const float* states_pool, const float* actions_pool,
                                 const float* logp_pool, const float* advantages_pool, const float* returns_pool, float* states_out,
@@ -261,6 +274,9 @@ int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const 
  * the gathered array [world][64].  Every rank must then issue the same sequence of wb_ppo_grad_allreduce_dev calls. */
 int32_t wb_comm_local_handle(wb_policy* p, void* handle64_out);
 int32_t wb_comm_connect(wb_policy* p, int32_t rank, int32_t world, const void* all_handles64);
+/* failed_out != 0: an exchange gave up waiting for a peer (bounded spin).  The slices that timed out were neither stored nor
+ * passed to Adam, every later exchange of the handle is a no-op on the device, and wb_ppo_train_dev / wb_ppo_grad_allreduce_dev
+ * return WB_ERR_COMM from then on (the status word is mapped host memory: the check costs nothing and needs no sync) */
 int32_t wb_comm_status(wb_policy* p, int32_t* connected_world_out, int32_t* failed_out);
 int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
                                   const float* advantages_dev, const float* returns_dev);

@@ -124,7 +124,9 @@ def lib() -> C.CDLL:
         "wb_comm_status": (C.c_int32, [vp, ip, ip]),
         "wb_ppo_grad_allreduce_dev": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp]),
         "wb_ppo_train_dev": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp]),
-        "wb_segment_returns_dev": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]),
+        "wb_segment_returns_dev": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]),
+        "wb_normalize_advantages_dev": (C.c_int32, [vp, C.c_int32, C.c_int64, C.c_int64, vp]),
+        "wb_normalize_stats_buffer": (C.c_int32, [vp, C.POINTER(vp), ip]),
         "wb_gather_minibatch_dev": (C.c_int32, [vp, C.c_int32] + [vp] * 11),
         "wb_ppo_grad": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
         "wb_ppo_grad_dev": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp]),

@@ -290,8 +290,9 @@ int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const u
   }
   const size_t np = (size_t)env->n_pad;
   std::vector<uint8_t> fm(np, (uint8_t)WB_METAL), wm(np, (uint8_t)WB_CARPET);
+  Material table[WB_MAX_MATERIALS];
   {
-    std::lock_guard<std::mutex> lock(g_mat_mutex);
+    std::lock_guard<std::mutex> lock(g_mat_mutex);  // held only for the table snapshot, not across the upload
     for (int i = 0; i < n_envs; i++) {
       if (floor_material_ids) fm[i] = floor_material_ids[i];
       if (walker_material_ids) wm[i] = walker_material_ids[i];
@@ -300,38 +301,49 @@ int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const u
         return fail(WB_ERR_INVALID, "env %d uses an unregistered material id", i);
       }
     }
-    WB_CUDA(upload_materials(g_materials, WB_MAX_MATERIALS));
+    memcpy(table, g_materials, sizeof(table));
   }
+  // any failure from here on releases everything allocated so far (wb_env_destroy) before returning
+#define WB_ENV_TRY(expr)                                                                    \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      wb_env_destroy(env);                                                                  \
+      return wb::fail(WB_ERR_CUDA, "wb_env_create: %s: %s", #expr, cudaGetErrorString(_e)); \
+    }                                                                                       \
+  } while (0)
+  WB_ENV_TRY(upload_materials(table, WB_MAX_MATERIALS));
   float floor10[10];
   FloorConst floor_const;
   build_scene_constants(env->init92, floor10);
   build_floor_constants(floor10, &floor_const);
-  WB_CUDA(upload_scene_constants(env->init92, &floor_const));
-  WB_CUDA(cudaMalloc(&env->d_state, sizeof(float) * kStateFloats * np));
-  WB_CUDA(cudaMalloc(&env->d_flags, sizeof(int32_t) * np));
-  WB_CUDA(cudaMalloc(&env->d_steps, sizeof(int32_t) * np));
-  WB_CUDA(cudaMalloc(&env->d_pos, sizeof(float) * 2 * np));
-  WB_CUDA(cudaMalloc(&env->d_floor_mat, np));
-  WB_CUDA(cudaMalloc(&env->d_walker_mat, np));
-  WB_CUDA(cudaMalloc(&env->d_axis_cache, sizeof(uint32_t) * np));
-  WB_CUDA(cudaMemset(env->d_axis_cache, 0, sizeof(uint32_t) * np));
-  WB_CUDA(cudaMalloc(&env->d_actions, sizeof(float) * WB_ACT * np));
-  WB_CUDA(cudaMalloc(&env->d_obs, sizeof(float) * WB_OBS * np));
-  WB_CUDA(cudaMalloc(&env->d_reward, sizeof(float) * np));
-  WB_CUDA(cudaMalloc(&env->d_done, np));
-  WB_CUDA(cudaMalloc(&env->d_mask, np));
-  WB_CUDA(cudaMemset(env->d_state, 0, sizeof(float) * kStateFloats * np));
-  WB_CUDA(cudaMemset(env->d_flags, 0, sizeof(int32_t) * np));
-  WB_CUDA(cudaMemset(env->d_steps, 0, sizeof(int32_t) * np));
-  WB_CUDA(cudaMemset(env->d_pos, 0, sizeof(float) * 2 * np));
-  WB_CUDA(cudaMemcpy(env->d_floor_mat, fm.data(), np, cudaMemcpyHostToDevice));
-  WB_CUDA(cudaMemcpy(env->d_walker_mat, wm.data(), np, cudaMemcpyHostToDevice));
+  WB_ENV_TRY(upload_scene_constants(env->init92, &floor_const));
+  WB_ENV_TRY(cudaMalloc(&env->d_state, sizeof(float) * kStateFloats * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_flags, sizeof(int32_t) * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_steps, sizeof(int32_t) * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_pos, sizeof(float) * 2 * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_floor_mat, np));
+  WB_ENV_TRY(cudaMalloc(&env->d_walker_mat, np));
+  WB_ENV_TRY(cudaMalloc(&env->d_axis_cache, sizeof(uint32_t) * np));
+  WB_ENV_TRY(cudaMemset(env->d_axis_cache, 0, sizeof(uint32_t) * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_actions, sizeof(float) * WB_ACT * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_obs, sizeof(float) * WB_OBS * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_reward, sizeof(float) * np));
+  WB_ENV_TRY(cudaMalloc(&env->d_done, np));
+  WB_ENV_TRY(cudaMalloc(&env->d_mask, np));
+  WB_ENV_TRY(cudaMemset(env->d_state, 0, sizeof(float) * kStateFloats * np));
+  WB_ENV_TRY(cudaMemset(env->d_flags, 0, sizeof(int32_t) * np));
+  WB_ENV_TRY(cudaMemset(env->d_steps, 0, sizeof(int32_t) * np));
+  WB_ENV_TRY(cudaMemset(env->d_pos, 0, sizeof(float) * 2 * np));
+  WB_ENV_TRY(cudaMemcpy(env->d_floor_mat, fm.data(), np, cudaMemcpyHostToDevice));
+  WB_ENV_TRY(cudaMemcpy(env->d_walker_mat, wm.data(), np, cudaMemcpyHostToDevice));
   // constructor state: walker first, floor last (Environment.cs:46-48), then InitialState
   if (int32_t rc = launch(env, kPhaseResetMasked | kPhaseFirstEpisode, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) {
     wb_env_destroy(env);
     return rc;
   }
-  WB_CUDA(cudaStreamSynchronize(env->stream));
+  WB_ENV_TRY(cudaStreamSynchronize(env->stream));
+#undef WB_ENV_TRY
   *out = env;
   return WB_OK;
 }

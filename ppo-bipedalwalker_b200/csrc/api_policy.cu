@@ -26,7 +26,9 @@ struct wb_policy {
   size_t stage_floats = 0;
   // fused reduce + all-reduce over NVLink peer memory (wb_comm_*)
   float* d_exch = nullptr;       // this rank's exchange buffer (kExchBytes), exported through CUDA IPC
-  uint32_t* d_comm_status = nullptr;
+  uint32_t* h_comm_status = nullptr;  // mapped pinned host word: set by reduce_exchange_kernel when a peer never arrived
+  uint32_t* d_comm_status = nullptr;  // its device alias
+  double* d_norm_stats = nullptr;     // [2][kNormCtas] partial sums of PPOAgent.Normalize (wb_normalize_advantages_dev)
   ExchPeers peers{};
   void* opened[kExchMaxWorld] = {};  // IPC mappings to close
   int comm_rank = -1, comm_world = 0;
@@ -77,6 +79,14 @@ static void fill_mlp_common(const wb_policy* p, MlpParams& m, int n, int mode) {
   m.batch_size = (float)p->hp.batch_size;
 }
 
+// a timed-out exchange leaves the ranks' weights out of step: refuse every later data-parallel update of this handle
+static int32_t comm_healthy(const wb_policy* p) {
+  if (*reinterpret_cast<volatile uint32_t*>(p->h_comm_status) != 0u)
+    return fail(WB_ERR_COMM, "a gradient exchange timed out (a peer never arrived): gradients were not applied for the affected slices "
+                             "and the replicas may have diverged; recreate the policy handles on every rank");
+  return WB_OK;
+}
+
 extern "C" {
 
 int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t* actor_kinds, const int32_t* actor_sizes,
@@ -96,15 +106,26 @@ int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t*
   cudaGetDevice(&p->device);
   cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
   if (hp) p->hp = *hp; else wb_hyperparams_default(&p->hp);
-  WB_CUDA(cudaMalloc(&p->d_params, sizeof(float) * kTotalParams));
-  WB_CUDA(cudaMalloc(&p->d_grads, sizeof(float) * kGradFloats));
-  WB_CUDA(cudaMalloc(&p->d_m, sizeof(float) * kTotalParams));
-  WB_CUDA(cudaMalloc(&p->d_v, sizeof(float) * kTotalParams));
-  WB_CUDA(cudaMalloc(&p->d_partials, sizeof(float) * kGradFloats * (size_t)p->sm_count));
-  WB_CUDA(cudaMemset(p->d_params, 0, sizeof(float) * kTotalParams));
-  WB_CUDA(cudaMemset(p->d_grads, 0, sizeof(float) * kGradFloats));
-  WB_CUDA(cudaMemset(p->d_m, 0, sizeof(float) * kTotalParams));
-  WB_CUDA(cudaMemset(p->d_v, 0, sizeof(float) * kTotalParams));
+  // (any failure below releases what was allocated so far: nothing leaks behind a failed create)
+  cudaError_t e = cudaMalloc(&p->d_params, sizeof(float) * kTotalParams);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_grads, sizeof(float) * kGradFloats);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_m, sizeof(float) * kTotalParams);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_v, sizeof(float) * kTotalParams);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_partials, sizeof(float) * kGradFloats * (size_t)p->sm_count);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_norm_stats, sizeof(double) * 2 * kNormCtas);
+  if (e == cudaSuccess) e = cudaHostAlloc(&p->h_comm_status, sizeof(uint32_t), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *p->h_comm_status = 0;
+    e = cudaHostGetDevicePointer(&p->d_comm_status, p->h_comm_status, 0);
+  }
+  if (e == cudaSuccess) e = cudaMemset(p->d_params, 0, sizeof(float) * kTotalParams);
+  if (e == cudaSuccess) e = cudaMemset(p->d_grads, 0, sizeof(float) * kGradFloats);
+  if (e == cudaSuccess) e = cudaMemset(p->d_m, 0, sizeof(float) * kTotalParams);
+  if (e == cudaSuccess) e = cudaMemset(p->d_v, 0, sizeof(float) * kTotalParams);
+  if (e != cudaSuccess) {
+    wb_policy_destroy(p);
+    return fail(WB_ERR_CUDA, "wb_policy_create: %s", cudaGetErrorString(e));
+  }
   *out = p;
   return WB_OK;
 }
@@ -118,7 +139,8 @@ int32_t wb_policy_destroy(wb_policy* p) {
   for (int r = 0; r < kExchMaxWorld; r++)
     if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
   cudaFree(p->d_exch);
-  cudaFree(p->d_comm_status);
+  if (p->h_comm_status) cudaFreeHost(p->h_comm_status);
+  cudaFree(p->d_norm_stats);
   cudaFree(p->d_partials);
   cudaFree(p->d_stage);
   delete p;
@@ -293,14 +315,32 @@ int32_t wb_policy_act_dev(wb_policy* p, int32_t n, const float* states_dev, uint
 }
 
 int32_t wb_segment_returns_dev(wb_policy* p, int32_t n_envs, int32_t horizon, const float* rewards_dev, const float* values_dev,
-                               const uint8_t* dones_dev, float* returns_dev, float* advantages_dev) {
+                               const uint8_t* dones_dev, const float* last_values_dev, float* returns_dev, float* advantages_dev) {
   WB_REQUIRE(p && rewards_dev && values_dev && dones_dev && returns_dev && advantages_dev, "null argument");
   WB_REQUIRE(n_envs > 0 && horizon > 0, "n_envs and horizon must be positive");
-  if (p->hp.normalize_advantages)
-    return fail(WB_ERR_UNSUPPORTED, "NormalizeAdvantages is per trajectory in the reference (PPOAgent.cs:461-472); the segment form does not define it");
-  WB_CUDA(launch_segment_returns(rewards_dev, values_dev, dones_dev, n_envs, horizon, p->hp.gamma, p->hp.lambda, p->hp.use_gae,
-                                 returns_dev, advantages_dev, p->stream));
+  WB_CUDA(launch_segment_returns(rewards_dev, values_dev, dones_dev, last_values_dev, n_envs, horizon, p->hp.gamma, p->hp.lambda,
+                                 p->hp.use_gae, returns_dev, advantages_dev, p->stream));
   p->launches++;
+  if (p->hp.normalize_advantages) return wb_normalize_advantages_dev(p, -1, (int64_t)n_envs * horizon, (int64_t)n_envs * horizon, advantages_dev);
+  return WB_OK;
+}
+
+int32_t wb_normalize_advantages_dev(wb_policy* p, int32_t stage, int64_t n_local, int64_t n_global, float* advantages_dev) {
+  WB_REQUIRE(p && advantages_dev, "null argument");
+  WB_REQUIRE(stage >= -1 && stage <= 2, "stage must be -1 (all), 0, 1 or 2");
+  WB_REQUIRE(n_local > 0 && n_global >= n_local, "n_local must be positive and n_global >= n_local");
+  const int first = stage < 0 ? 0 : stage, last = stage < 0 ? 2 : stage;
+  for (int st = first; st <= last; st++) {
+    WB_CUDA(launch_normalize_stage(advantages_dev, (long)n_local, (double)n_global, st, p->hp.epsilon, p->d_norm_stats, p->stream));
+    p->launches++;
+  }
+  return WB_OK;
+}
+
+int32_t wb_normalize_stats_buffer(wb_policy* p, void** dev_ptr_out, int32_t* n_doubles_out) {
+  WB_REQUIRE(p && dev_ptr_out && n_doubles_out, "null argument");
+  *dev_ptr_out = p->d_norm_stats;
+  *n_doubles_out = 2 * kNormCtas;
   return WB_OK;
 }
 
@@ -365,8 +405,6 @@ int32_t wb_comm_local_handle(wb_policy* p, void* handle64_out) {
   if (!p->d_exch) {
     WB_CUDA(cudaMalloc(&p->d_exch, kExchBytes));
     WB_CUDA(cudaMemset(p->d_exch, 0, kExchBytes));
-    WB_CUDA(cudaMalloc(&p->d_comm_status, sizeof(uint32_t)));
-    WB_CUDA(cudaMemset(p->d_comm_status, 0, sizeof(uint32_t)));
     WB_CUDA(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t h;
@@ -400,12 +438,8 @@ int32_t wb_comm_connect(wb_policy* p, int32_t rank, int32_t world, const void* a
 int32_t wb_comm_status(wb_policy* p, int32_t* connected_world_out, int32_t* failed_out) {
   WB_REQUIRE(p && connected_world_out && failed_out, "null argument");
   *connected_world_out = p->comm_world;
-  uint32_t st = 0;
-  if (p->d_comm_status) {
-    WB_CUDA(cudaStreamSynchronize(p->stream));
-    WB_CUDA(cudaMemcpy(&st, p->d_comm_status, sizeof(st), cudaMemcpyDeviceToHost));
-  }
-  *failed_out = (int32_t)st;
+  WB_CUDA(cudaStreamSynchronize(p->stream));
+  *failed_out = (int32_t)*reinterpret_cast<volatile uint32_t*>(p->h_comm_status);
   return WB_OK;
 }
 
@@ -415,6 +449,7 @@ int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_d
   WB_REQUIRE(n > 0, "n must be positive");
   WB_REQUIRE(p->hp.batch_size > 0, "batch_size must be positive");
   WB_REQUIRE(p->comm_world >= 1, "not connected: call wb_comm_local_handle / wb_comm_connect on every rank first");
+  if (int32_t rc = comm_healthy(p)) return rc;
   MlpParams m;
   fill_mlp_common(p, m, n, kModeGrad);
   m.states = states_dev;
@@ -454,10 +489,7 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
   WB_REQUIRE(p && states_dev && actions_dev && old_logp_dev && advantages_dev && returns_dev, "null argument");
   WB_REQUIRE(n > 0, "n must be positive");
   WB_REQUIRE(p->hp.batch_size > 0, "batch_size must be positive");
-  if (!p->d_comm_status) {
-    WB_CUDA(cudaMalloc(&p->d_comm_status, sizeof(uint32_t)));
-    WB_CUDA(cudaMemset(p->d_comm_status, 0, sizeof(uint32_t)));
-  }
+  if (int32_t rc = comm_healthy(p)) return rc;
   MlpParams m;
   fill_mlp_common(p, m, n, kModeGrad);
   m.states = states_dev;

@@ -106,11 +106,15 @@ int32_t wb_scene_create(int32_t n_envs, const wb_body_desc* bodies, int32_t n_bo
   std::vector<float> all((size_t)s->rows * s->n_pad);
   for (int r = 0; r < s->rows; r++)
     for (int i = 0; i < s->n_pad; i++) all[(size_t)r * s->n_pad + i] = one[r];
-  WB_CUDA(cudaMalloc(&s->d_state, sizeof(float) * all.size()));
-  WB_CUDA(cudaMalloc(&s->d_collided, sizeof(int32_t) * s->n_pad));
-  WB_CUDA(cudaMalloc(&s->d_torques, sizeof(float) * (size_t)s->n * (n_joints > 0 ? n_joints : 1)));
-  WB_CUDA(cudaMemcpy(s->d_state, all.data(), sizeof(float) * all.size(), cudaMemcpyHostToDevice));
-  WB_CUDA(cudaMemset(s->d_collided, 0, sizeof(int32_t) * s->n_pad));
+  cudaError_t e = cudaMalloc(&s->d_state, sizeof(float) * all.size());
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_collided, sizeof(int32_t) * s->n_pad);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_torques, sizeof(float) * (size_t)s->n * (n_joints > 0 ? n_joints : 1));
+  if (e == cudaSuccess) e = cudaMemcpy(s->d_state, all.data(), sizeof(float) * all.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(s->d_collided, 0, sizeof(int32_t) * s->n_pad);
+  if (e != cudaSuccess) {  // nothing leaks behind a failed create
+    wb_scene_destroy(s);
+    return fail(WB_ERR_CUDA, "wb_scene_create: %s", cudaGetErrorString(e));
+  }
   *out = s;
   return WB_OK;
 }

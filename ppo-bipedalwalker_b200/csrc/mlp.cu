@@ -474,16 +474,21 @@ __global__ void returns_kernel(const float* rewards, const float* values, int n,
 // The same recurrences over a time-major rollout buffer [T][N] of N lockstep environments (the reference trains on one
 // episode of one environment, PPOAgent.cs:147; here every environment contributes the fragments of its episodes that fall
 // inside the T-step segment).  One thread per environment, reverse scan; a step with done != 0 is the LAST step of its
-// episode, so the recurrence restarts there exactly like at the end of a trajectory (next return / next value = 0), and the
-// segment end is treated the same way (truncation).
+// episode, so the recurrence restarts there exactly like at the end of a trajectory (next return / next value = 0).
+// The segment end: an episode that is still running when the segment ends is NOT over, so its tail must not be scored as if
+// the return stopped there.  With `last_values` (the critic's estimate V(s_T) of the observation AFTER the last step) the scan
+// starts from it -- next return = next value = V(s_T) unless dones[T-1] is set -- which is the standard bootstrap for a
+// fixed-horizon rollout; the reference never needs it because it only trains on complete episodes.  last_values == nullptr
+// keeps the reference's trajectory-end semantics at the segment end (truncation: the form the oracle comparison uses).
 __global__ void segment_returns_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
-                                       int n_envs, int T, float gamma, float lambda, int use_gae, float* __restrict__ returns,
-                                       float* __restrict__ advantages) {
+                                       const float* __restrict__ last_values, int n_envs, int T, float gamma, float lambda, int use_gae,
+                                       float* __restrict__ returns, float* __restrict__ advantages) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_envs) return;
+  const float boot = last_values != nullptr ? last_values[e] : 0.0f;
   if (use_gae) {
     const float next_gae = 0.0f;  // never updated in the reference (PPOAgent.cs:414-444)
-    float next_value = 0.0f;
+    float next_value = boot;
     for (int t = T - 1; t >= 0; t--) {
       const size_t i = (size_t)t * n_envs + e;
       if (dones[i]) next_value = 0.0f;
@@ -495,7 +500,7 @@ __global__ void segment_returns_kernel(const float* __restrict__ rewards, const 
       returns[i] = __fadd_rn(gae, cur);
     }
   } else {
-    float g = 0.0f;
+    float g = boot;
     for (int t = T - 1; t >= 0; t--) {
       const size_t i = (size_t)t * n_envs + e;
       if (dones[i]) g = 0.0f;
@@ -504,6 +509,54 @@ __global__ void segment_returns_kernel(const float* __restrict__ rewards, const 
       advantages[i] = __fsub_rn(g, values[i]);
     }
   }
+}
+
+// PPOAgent.Normalize (PPOAgent.cs:461-472) over a pool of advantages, in three launches so that a data-parallel caller can
+// all-reduce the two double sums in between (stats[0] = sum x, stats[1] = sum ((double)(x - mean))^2, both accumulated in
+// double like List<float>.Average() / Sum(Math.Pow(value - mean, 2)); the summation order is a fixed tree instead of the
+// reference's left-to-right loop, a difference of ~1e-16 relative in the double sums before they are rounded to float).
+//   stage 0: partial sums of x                         -> stats[0 .. kNormCtas)
+//   stage 1: mean = (float)(sum / count); partial sums of ((double)(x - mean))^2 -> stats[kNormCtas .. 2 kNormCtas)
+//   stage 2: std = (float)sqrt(sum2 / count); x = (x - mean) / (std + epsilon)
+// Every consumer adds the kNormCtas partials in index order, so the totals are identical wherever they are formed (a
+// data-parallel caller all-reduces the partial arrays element by element between the stages).
+__device__ __forceinline__ double norm_total(const double* stats, int stage, double* s_bcast) {
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int g = 0; g < kNormCtas; g++) t += stats[stage * kNormCtas + g];
+    *s_bcast = t;
+  }
+  __syncthreads();
+  return *s_bcast;
+}
+__global__ void __launch_bounds__(kNormThreads) normalize_sums_kernel(const float* __restrict__ x, long n, double count, int stage, double* stats) {
+  __shared__ double red[kNormThreads];
+  __shared__ double s_sum;
+  float mean = 0.0f;
+  if (stage == 1) mean = (float)(norm_total(stats, 0, &s_sum) / count);
+  double acc = 0.0;
+  for (long i = (long)blockIdx.x * kNormThreads + threadIdx.x; i < n; i += (long)kNormCtas * kNormThreads) {
+    if (stage == 0) {
+      acc += (double)x[i];
+    } else {
+      const double d = (double)__fsub_rn(x[i], mean);
+      acc += d * d;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = kNormThreads / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) stats[stage * kNormCtas + blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256) normalize_apply_kernel(float* __restrict__ x, long n, double count, float epsilon, const double* __restrict__ stats) {
+  __shared__ double s_sum, s_sum2;
+  const float mean = (float)(norm_total(stats, 0, &s_sum) / count);
+  const float sd = (float)sqrt(norm_total(stats, 1, &s_sum2) / count);
+  const float div = __fadd_rn(sd, epsilon);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] = __fdiv_rn(__fsub_rn(x[i], mean), div);
 }
 
 // PPOAgent.CreateBatches (PPOAgent.cs:501-540) on the device: rows index[b] of the rollout pool -> a contiguous minibatch.
@@ -524,10 +577,18 @@ __global__ void gather_minibatch_kernel(const int32_t* __restrict__ index, int B
 }
 
 // ---------------------------------------------------------------- host side
-cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, int n_envs, int T, float gamma,
-                                   float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream) {
-  segment_returns_kernel<<<(n_envs + 127) / 128, 128, 0, stream>>>(rewards, values, dones, n_envs, T, gamma, lambda, use_gae, returns,
-                                                                   advantages);
+cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int n_envs,
+                                   int T, float gamma, float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream) {
+  segment_returns_kernel<<<(n_envs + 127) / 128, 128, 0, stream>>>(rewards, values, dones, last_values, n_envs, T, gamma, lambda, use_gae,
+                                                                   returns, advantages);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_normalize_stage(float* x, long n_local, double count_global, int stage, float epsilon, double* stats, cudaStream_t stream) {
+  if (stage == 0 || stage == 1)
+    normalize_sums_kernel<<<kNormCtas, kNormThreads, 0, stream>>>(x, n_local, count_global, stage, stats);
+  else
+    normalize_apply_kernel<<<296, 256, 0, stream>>>(x, n_local, count_global, epsilon, stats);
   return cudaGetLastError();
 }
 
@@ -611,7 +672,11 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
     acc.w += __shfl_xor_sync(0xFFFFFFFFu, acc.w, m);
   }
   float4 s = acc;
+  bool ok = true;
   if (world > 1) {  // (world is a kernel argument: uniform)
+    // a previous exchange of this handle timed out: the ranks' weights can no longer be assumed identical -- every later launch
+    // is a no-op (no store, no Adam) until the host has seen the status word (wb_comm_status / wb_ppo_train_dev refuse)
+    if (__syncthreads_or(threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(status) != 0u)) return;  // (CTA-uniform)
     if (in) {
       // push my slice into slot [par][rank] of every rank (NVLink stores; r == rank is local); the 4 lanes of an element share the peers
       for (int r = part; r < world; r += 4) reinterpret_cast<float4*>(peers.base[r] + exch_slot_offset(par, rank))[i4] = acc;
@@ -619,18 +684,22 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < world) st_release_sys(exch_flag(peers.base[threadIdx.x], par, rank, blockIdx.x), epoch);
+    bool timed_out = false;
     if ((int)threadIdx.x < world) {  // wait for rank threadIdx.x's slice in MY buffer
       const uint32_t* f = exch_flag(peers.base[rank], par, threadIdx.x, blockIdx.x);
       long spins = 0;
       while (ld_acquire_sys(f) != epoch) {
         if (++spins > (1L << 31)) {  // a peer never arrived (crashed?): give up loudly instead of hanging the GPU
-          atomicExch(status, 1u);
+          *reinterpret_cast<volatile uint32_t*>(status) = 1u;  // (mapped host memory: the host sees it without a copy)
+          __threadfence_system();
+          timed_out = true;
           break;
         }
       }
     }
-    __syncthreads();
-    if (in && part == 0) {
+    // a slice whose peers did not all arrive holds stale slot data: it must neither be stored nor reach Adam
+    ok = __syncthreads_or(timed_out) == 0;
+    if (ok && in && part == 0) {
       s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < world; r++) {  // rank order on every rank: bit-identical sums
         const float4 v = __ldcg(reinterpret_cast<const float4*>(peers.base[rank] + exch_slot_offset(par, r)) + i4);
@@ -641,7 +710,7 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
       }
     }
   }
-  if (in && part == 0) {
+  if (ok && in && part == 0) {
     reinterpret_cast<float4*>(grads)[i4] = s;
     if (do_adam) {  // NeuralNetwork.Optimise fused behind the reduction: the gradient never makes another round trip
       const float g[4] = {s.x, s.y, s.z, s.w};

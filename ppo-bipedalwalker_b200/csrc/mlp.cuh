@@ -93,8 +93,13 @@ __host__ __device__ inline uint32_t* exch_flag(float* base, int parity, int rank
 cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
                                    uint32_t epoch, uint32_t* status, const AdamParams* adam, cudaStream_t stream);
 
-cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, int n_envs, int T, float gamma,
-                                   float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream);
+// last_values: V(s_T) per environment (bootstrap of a segment that ends mid-episode) or nullptr (truncate like a trajectory end)
+cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int n_envs,
+                                   int T, float gamma, float lambda, int use_gae, float* returns, float* advantages, cudaStream_t stream);
+// PPOAgent.Normalize over a pool, three stages (0: sum, 1: squared deviations, 2: apply); stats = double[2 * kNormCtas]
+constexpr int kNormCtas = 128;
+constexpr int kNormThreads = 256;
+cudaError_t launch_normalize_stage(float* x, long n_local, double count_global, int stage, float epsilon, double* stats, cudaStream_t stream);
 cudaError_t launch_gather_minibatch(const int32_t* index, int B, const float* states, const float* actions, const float* logp,
                                     const float* adv, const float* ret, float* o_states, float* o_actions, float* o_logp, float* o_adv,
                                     float* o_ret, cudaStream_t stream);

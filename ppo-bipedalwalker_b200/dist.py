@@ -21,8 +21,8 @@ def shard_range(n_total: int, rank: int, world_size: int):
 class DeviceBuffer:
     """Zero-copy view of a raw device pointer for torch (`torch.as_tensor(DeviceBuffer(...), device='cuda')`)."""
 
-    def __init__(self, ptr: int, n_floats: int):
-        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 def grad_tensor(agent):
@@ -30,6 +30,18 @@ def grad_tensor(agent):
     import torch
     ptr, n = agent.grad_buffer()
     return torch.as_tensor(DeviceBuffer(ptr, n), device=f"cuda:{torch.cuda.current_device()}")
+
+
+def norm_stats_tensor(agent):
+    """The partial-sum buffer of PPOAgent.Normalize (double[2 * 128]) as a torch CUDA tensor (no copy)."""
+    import ctypes as C
+
+    import torch
+
+    from ._lib import check, lib
+    p, n = C.c_void_p(), C.c_int32(0)
+    check(lib().wb_normalize_stats_buffer(agent._h, C.byref(p), C.byref(n)))
+    return torch.as_tensor(DeviceBuffer(p.value, n.value, "<f8"), device=f"cuda:{torch.cuda.current_device()}")
 
 
 def allreduce_sum_(tensor):

@@ -7,7 +7,10 @@ values, returns, advantages, Epochs x shuffled mini-batches of Train(Batch) -- r
   rollout   `horizon` env-steps; per env-step TWO kernel launches: wb_policy_act_dev (actor + critic + Philox Box-Muller sampling +
             log-probabilities) and wb_env_step_dev (the fused physics step with auto-reset).  The trajectory (states, UNCLIPPED
             actions and their log-probabilities -- Environment.cs:87-88 --, rewards, dones, values) stays in HBM, time-major.
-  update    wb_segment_returns_dev (MC return / the reference's GAE per episode fragment), then `epochs` x (pool / minibatch)
+  update    wb_segment_returns_dev (MC return / the reference's GAE per episode fragment; a fragment that is still running at the
+            end of the horizon is bootstrapped with the critic's value of the next observation -- the reference never meets this
+            case because it trains on complete episodes only; `bootstrap=False` truncates instead), optionally
+            PPOAgent.Normalize over the global pool (two 2 KB all-reduces), then `epochs` x (pool / minibatch)
             mini-batches: index permutation (sampling without replacement, remainder dropped, PPOAgent.cs:501-540) ->
             wb_gather_minibatch_dev -> wb_ppo_train_dev (gradient kernel + ONE kernel that reduces the partial gradients,
             all-reduces the 6 152-float buffer over NVLink peer memory and applies Adam; NCCL all-reduce as the fallback).
@@ -33,10 +36,13 @@ from .ppo import PPOAgent
 class VectorPPO:
     def __init__(self, n_envs_global: int, horizon: int = 64, minibatch_global: int = 65536, epochs: int = 1,
                  floor="Metal", walker="Carpet", hp: Hyperparams | None = None, seed: int = 0, policy_variant: int | None = None,
-                 fused_allreduce: bool = True):
+                 fused_allreduce: bool = True, bootstrap: bool = True):
         import torch
         self.torch = torch
         self.rank, self.local_rank, self.world = _dist.world()
+        # equal shards: every rank must issue the same number of gradient exchanges per update (an uneven split would leave
+        # the fused exchange waiting for a peer that has no mini-batch left)
+        assert n_envs_global % self.world == 0, "n_envs_global must be a multiple of the number of ranks"
         lo, hi = _dist.shard_range(n_envs_global, self.rank, self.world)
         self.n = hi - lo
         self.env_offset = lo
@@ -48,6 +54,7 @@ class VectorPPO:
         self.pool_local = self.n * self.T
         assert self.pool_local >= self.mb_local, "local rollout pool smaller than the local mini-batch share"
         self.epochs = epochs
+        self.bootstrap = bool(bootstrap)
         self.seed = seed
         self.hp = hp if hp is not None else default_hyperparams()
         self.hp.batch_size = minibatch_global  # the divisor B of every per-sample gradient (PPOAgent.cs:326,333)
@@ -70,6 +77,8 @@ class VectorPPO:
         self.obs = torch.from_numpy(self.env.get_obs()).to(dev)  # Environment.InitialState
         self.mb = [torch.empty(self.mb_local, OBS, **f32), torch.empty(self.mb_local, ACT, **f32), torch.empty(self.mb_local, ACT, **f32),
                    torch.empty(self.mb_local, **f32), torch.empty(self.mb_local, **f32)]
+        self.last_values = torch.empty(n, **f32)
+        self.norm_stats = _dist.norm_stats_tensor(self.agent)
         self.grad_view = _dist.grad_tensor(self.agent)
         # multi-GPU: the gradient all-reduce is fused into the reduction kernel (NVLink peer memory, dist.connect_peers);
         # fused_allreduce=False keeps the NCCL all-reduce (same result, one more launch + the NCCL latency per mini-batch)
@@ -97,8 +106,24 @@ class VectorPPO:
         torch = self.torch
         L = lib()
         h = self.agent._h
-        check(L.wb_segment_returns_dev(h, self.n, self.T, ptr(self.rewards), ptr(self.values), ptr(self.dones), ptr(self.returns),
+        last = None
+        if self.bootstrap:  # V(s_T): one more critic forward on the observation the rollout ended on
+            check(L.wb_policy_forward_dev(h, self.n, ptr(self.obs), None, ptr(self.last_values)))
+            last = self.last_values
+        normalize = bool(self.hp.normalize_advantages)
+        if normalize and self.world > 1:
+            self.hp.normalize_advantages = 0  # the stages run below with an all-reduce in between
+            self.agent.set_hyperparams(self.hp)
+        check(L.wb_segment_returns_dev(h, self.n, self.T, ptr(self.rewards), ptr(self.values), ptr(self.dones), ptr(last), ptr(self.returns),
                                        ptr(self.adv)))
+        if normalize and self.world > 1:
+            self.hp.normalize_advantages = 1
+            self.agent.set_hyperparams(self.hp)
+            pool_global = self.pool_local * self.world
+            for stage in (0, 1, 2):  # PPOAgent.Normalize over the GLOBAL pool: sum -> all-reduce -> squared deviations -> all-reduce -> apply
+                check(L.wb_normalize_advantages_dev(h, stage, self.pool_local, pool_global, ptr(self.adv)))
+                if stage < 2:
+                    _dist.allreduce_sum_(self.norm_stats)
         S, A, LP = self.states.view(-1, OBS), self.actions.view(-1, ACT), self.logp.view(-1, ACT)
         ADV, RET = self.adv.view(-1), self.returns.view(-1)
         n_mb = self.pool_local // self.mb_local
@@ -115,6 +140,12 @@ class VectorPPO:
                     check(L.wb_ppo_grad_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
                     _dist.allreduce_sum_(self.grad_view)
                     check(L.wb_adam_step(h))
+        if self.fused and self.world > 1:
+            # a peer that never arrived leaves stale slices unapplied and the replicas out of step: fail loudly, once per update
+            world, failed = C.c_int32(0), C.c_int32(0)
+            check(L.wb_comm_status(h, C.byref(world), C.byref(failed)))
+            if failed.value:
+                raise RuntimeError("fused gradient exchange timed out: a rank never arrived; the replicas' weights may differ")
         losses = self.grad_view[-3:].clone()  # [sum g_V, sum mean_k g_mu, skipped] of the last mini-batch (PPOAgent.cs:331-332)
         return n_mb * self.epochs, losses
 

@@ -119,26 +119,58 @@ class _Net:
             p += out * inp
             b = flat[p:p + out]
             p += out
-            lines.append("W " + " ".join(repr(float(x)) for x in w) + " B " + " ".join(repr(float(x)) for x in b))
+            lines.append("W " + " ".join(net_float_str(x) for x in w) + " B " + " ".join(net_float_str(x) for x in b))
         return lines
 
-    # NeuralNetwork.Load / DenseLayer.Load (NeuralNetwork.cs:94-115, DenseLayer.cs:55-69)
+    # NeuralNetwork.Load / ValidateWeights / DenseLayer.Load / Matrix.Load (NeuralNetwork.cs:94-150, DenseLayer.cs:55-69, Matrix.cs:109-130)
     def Load(self, contents: list[str]) -> bool:
+        """Like the reference: the structure line must match, EVERY line is validated (each token parses as a float) before any
+        layer is touched, then the dense lines that are present are loaded in order -- a file with fewer lines than layers
+        updates the leading layers only; values beyond a layer's size are ignored (Matrix.Load reads height x length of them).
+        Where the reference would throw (more lines than layers, too few values in a line) this returns False and loads nothing."""
         if len(contents) < 2 or contents[0] != self.structure:
             return False
-        parts = []
+        lines = contents[1:]
+        if len(lines) > len(self.shapes):
+            return False
+        parsed = []
         try:
-            for line, (out, inp) in zip(contents[1:], self.shapes):
+            for line in lines:  # ValidateWeights
                 wi, bi = line.index("W") + 2, line.index("B") + 2
-                w = np.array(line[wi:bi - 3].split(), np.float32)
-                b = np.array(line[bi:].split(), np.float32)
-                if w.size != out * inp or b.size != out:
-                    return False
-                parts += [w, b]
+                w = [float(tok) for tok in line[wi:bi - 3].split()]
+                b = [float(tok) for tok in line[bi:].split()]
+                parsed.append((np.array(w, np.float32), np.array(b, np.float32)))
         except ValueError:
             return False
-        self.set_flat(np.concatenate(parts))
+        flat = self.get_flat()
+        p = 0
+        for (w, b), (out, inp) in zip(parsed, self.shapes):
+            if w.size < out * inp or b.size < out:
+                return False
+            flat[p:p + out * inp] = w[:out * inp]
+            p += out * inp
+            flat[p:p + out] = b[:out]
+            p += out
+        self.set_flat(flat)
         return True
+
+
+def net_float_str(x) -> str:
+    """float.ToString() of .NET Core 3.0+ (what Matrix.Save joins, Matrix.cs:133-136): the shortest string that round-trips the
+    binary32 value; plain decimal notation for 1e-4 <= |x| < 1e7, otherwise d.dddE+XX / d.dddE-XX with at least two exponent digits."""
+    v = np.float32(x)
+    if np.isnan(v):
+        return "NaN"
+    if np.isinf(v):
+        return "Infinity" if v > 0 else "-Infinity"
+    if v == 0:
+        return "-0" if np.signbit(v) else "0"
+    sci = np.format_float_scientific(v, unique=True, trim="-", exp_digits=2)  # e.g. 1.2345e-06
+    mant, exp = sci.split("e")
+    e = int(exp)
+    if -5 < e < 7:  # the "G" rule: fixed-point iff -5 < exponent < precision (7 for Single)
+        return np.format_float_positional(v, unique=True, trim="-")
+    return f"{mant}E{'+' if e >= 0 else '-'}{abs(e):02d}"
 
 
 class PPOAgent:
@@ -285,35 +317,5 @@ class PPOAgent:
         return self.critic.Save(), self.actor.Save()
 
 
-def smoke_policy(O) -> None:
-    """Tiny forward + PPO gradient + Adam on cuda:0 against the oracle (called from __graft_entry__.smoke)."""
-    rng = np.random.default_rng(3)
-    agent = PPOAgent(seed=5)
-    actor = O.Net(12, O.ACTOR_LAYERS)
-    critic = O.Net(12, O.CRITIC_LAYERS)
-    actor.set_params(agent.actor.get_flat())
-    critic.set_params(agent.critic.get_flat())
-    n = 64
-    states = rng.normal(size=(n, 12)).astype(np.float32)
-    hp = O.hyper_defaults()
-    mean, value = agent.FeedForward(states)
-    rmean, rvalue = actor.forward(states), critic.forward(states)[:, 0]
-    assert np.allclose(mean, rmean, rtol=1e-5, atol=1e-6) and np.allclose(value, rvalue, rtol=1e-5, atol=1e-6)
-    std = np.exp(np.float32(-1.0))
-    actions = (rmean + std * rng.normal(size=(n, 4))).astype(np.float32)
-    old_logp = (-0.5 * ((actions - rmean) / std) ** 2 + 0.081 + 0.1 * rng.normal(size=(n, 4))).astype(np.float32)
-    adv = rng.normal(size=n).astype(np.float32)
-    ret = rng.normal(size=n).astype(np.float32) * 5
-    agent.TrainBatch(states, actions, old_logp, adv, ret)
-    O.ppo_train_batch(actor, critic, hp, states, actions, old_logp, adv, ret, optimise=True)
-    ga, gc = agent.actor.get_grads(), agent.critic.get_grads()
-    ra, rc = actor.get_grads(), critic.get_grads()
-    err = max(np.abs(ga - ra).max() / (np.abs(ra).max() + 1e-30), np.abs(gc - rc).max() / (np.abs(rc).max() + 1e-30))
-    assert err < 1e-4, f"PPO gradient mismatch {err}"
-    werr = np.abs(agent.actor.get_flat() - actor.get_params()).max()
-    assert werr < 1e-5, f"Adam weight mismatch {werr}"
-    print(f"smoke: PPO grad rel err {err:.2e}, post-Adam weight abs err {werr:.2e}; kernel launches = {agent.launch_count()}")
-
-
-__all__ = ["PPOAgent", "Trajectory", "ParseLayers", "xavier_flat", "smoke_policy", "DEFAULT_ACTOR", "DEFAULT_CRITIC", "DENSE",
+__all__ = ["PPOAgent", "Trajectory", "ParseLayers", "xavier_flat", "net_float_str", "DEFAULT_ACTOR", "DEFAULT_CRITIC", "DENSE",
            "RELU", "LEAKYRELU", "TANH"]

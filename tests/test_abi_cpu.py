@@ -101,3 +101,81 @@ def test_header_is_plain_c99_and_a_c_program_links_and_is_refused_without_a_gpu(
         pytest.skip("a CUDA device is present (tests/test_physics_gpu.py runs the program)")
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 3 and "no CPU fallback" in res.stderr
+
+
+def _csharp_dir():
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ppo-bipedalwalker_b200", "csharp")
+
+
+def test_csharp_binding_declares_exactly_the_header_exports(wb):
+    """ppo-bipedalwalker_b200/csharp/WalkerB200Native.cs holds one [DllImport] per function of include/walker_b200.h (no more, no
+    fewer, apart from the documented pinned-pointer overload), generated by scripts/gen_pinvoke.py: regenerating it from the
+    header reproduces the committed file byte for byte, and every declaration has the header's arity."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_pinvoke", os.path.join(root, "scripts", "gen_pinvoke.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(_csharp_dir(), "WalkerB200Native.cs")).read()
+    assert text == gen.render(), "WalkerB200Native.cs is stale: run `python scripts/gen_pinvoke.py`"
+    declared = re.findall(r"\[DllImport\(Lib\)\] public static extern \w+ (wb_[a-z0-9_]+)\(([^)]*)\);", text)
+    names = [n for n, _ in declared]
+    assert sorted(names) == wb.declared_symbols() and len(set(names)) == len(names)
+    arity = {name: len(params) for _, name, params in gen.prototypes()}
+    for name, params in declared:
+        assert len([p for p in params.split(",") if p.strip()]) == arity[name], name
+    overloads = re.findall(r'EntryPoint = "(wb_[a-z0-9_]+)"', text)
+    assert overloads == ["wb_env_step"]
+
+
+def test_csharp_structs_mirror_the_c_layouts(wb):
+    """The blittable C# structs list the same number of 4-byte fields, in the same order of types, as the C structs."""
+    header = open(os.path.join(os.path.dirname(_csharp_dir()), "..", "include", "walker_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    cs = open(os.path.join(_csharp_dir(), "WalkerB200Native.cs")).read()
+
+    def c_fields(name):
+        body = re.search(r"typedef struct \{([^}]*)\} " + name + ";", header).group(1)
+        out = []
+        for ctype, names in re.findall(r"(int32_t|uint32_t|float)\s+([^;]+);", body):
+            out += [{"int32_t": "int", "uint32_t": "uint", "float": "float"}[ctype]] * len(names.split(","))
+        return out
+
+    def cs_fields(name):
+        body = re.search(r"public struct " + name + r"\s*(?://[^\n]*)?\s*\{(.*?)\n?\}", cs, flags=re.S).group(1)
+        out = []
+        for ctype, names in re.findall(r"public (int|uint|float) ([^;(]+);", body):
+            out += [ctype] * len(names.split(","))
+        return out
+
+    for c_name, cs_name in [("wb_hyperparams", "WbHyperparams"), ("wb_body_desc", "WbBodyDesc"), ("wb_joint_desc", "WbJointDesc"),
+                            ("wb_pair_trace", "WbPairTrace"), ("wb_joint_trace", "WbJointTrace")]:
+        assert c_fields(c_name) == cs_fields(cs_name), (c_name, c_fields(c_name), cs_fields(cs_name))
+    assert C.sizeof(wb.Hyperparams) == 4 * len(c_fields("wb_hyperparams"))
+
+
+def test_csharp_shim_covers_the_reference_surface():
+    """The shim classes keep the reference's method names for this path: Environment.Update(float) / StepObjects /
+    InitialState / GetConsoleInformation, the Walker and PPOAgent surfaces, and the two plugin adapters; every wb_* call they make
+    exists in the generated binding."""
+    d = _csharp_dir()
+    env = open(os.path.join(d, "GpuEnvironment.cs")).read()
+    for sig in ["public void Update(float deltaTime)", "public void StepObjects(float deltaTime)", "public void InitialState()",
+                "GetConsoleInformation()", "public GpuWalker Walker(int index)"]:
+        assert sig in env, sig
+    walker = open(os.path.join(d, "GpuWalker.cs")).read()
+    for sig in ["GetActions(PPO.Matrix state, out PPO.Matrix logProbabilities)", "TakeActions(PPO.Matrix actions)",
+                "Train(Trajectory trajectory, Renderer renderer)", "GetState()", "GetJoints()", "GetPosition()", "GetChangeInPosition()",
+                "public bool Terminal", "Reset()", "CreateCreature()", "Update()"]:
+        assert sig in walker, sig
+    agent = open(os.path.join(d, "GpuPPOAgent.cs")).read()
+    for sig in ["public GpuPPOAgent(int stateSize, int actionSize)", "SampleActions(Matrix state, out Matrix logProbabilities, out Matrix mean, out Matrix std)",
+                "public void Train(Trajectory trajectory, Renderer renderer)", "public void Save()", "public void Load(string type)"]:
+        assert sig in agent, sig
+    adapters = open(os.path.join(d, "Adapters.cs")).read()
+    assert "IdOf(IMaterial material)" in adapters and "wb_material_register" in adapters and "wb_scene_create" in adapters
+    binding = open(os.path.join(d, "WalkerB200Native.cs")).read()
+    bound = set(re.findall(r"extern \w+ (wb_[a-z0-9_]+)\(", binding))
+    for text in (env, walker, agent, adapters):
+        for call in re.findall(r"Wb\.(wb_[a-z0-9_]+)\(", text):
+            assert call in bound, call

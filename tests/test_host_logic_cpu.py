@@ -174,3 +174,17 @@ def test_refharness_glue_exports_and_compares_the_golden_rollout(tmp_path):
     assert ok.returncode == 0 and "pinned" in ok.stdout
     res = subprocess.run([sys.executable, script, "compare", str(tmp_path / "bad.txt")], capture_output=True, text=True)
     assert res.returncode == 1 and "env-step 10, walker 3" in res.stdout and "LLU.velocity.x" in res.stdout
+
+
+def test_weight_values_print_like_dotnet_float_tostring(wb):
+    """Matrix.Save joins float.ToString() (Matrix.cs:133-136): shortest round-trip digits, decimal notation from 1e-4 up to 1e7,
+    otherwise E+XX / E-XX -- so a .weights file written here is byte-compatible with one the reference writes."""
+    import numpy as np
+    from ppo_bipedalwalker_b200.ppo import net_float_str
+    cases = {0.1: "0.1", -0.25: "-0.25", 1.0: "1", 0.0: "0", 1e-5: "1E-05", 9.999999e-6: "9.999999E-06", 1234567.0: "1234567",
+             1e7: "1E+07", 12345678.0: "1.2345678E+07", 3.4028235e38: "3.4028235E+38", 0.10000000149011612: "0.1", 1.5e-45: "1E-45"}
+    for value, text in cases.items():
+        assert net_float_str(np.float32(value)) == text, (value, net_float_str(np.float32(value)), text)
+    rng = np.random.default_rng(0)
+    for x in (rng.normal(size=2000) * 10.0 ** rng.integers(-8, 9, 2000)).astype(np.float32):
+        assert np.float32(float(net_float_str(x).replace("E", "e"))) == x  # round-trips exactly

@@ -115,6 +115,58 @@ def test_contact_stress_all_materials(gpu, O):
     assert_state_equal(env, ref, "stress")
 
 
+def test_contact_stress_sweep_at_baseline_size(gpu, O):
+    """BASELINE configs[4] at its full size: 16 384 walkers, 2 048 per floor material (Ice ... SuperRubber), every body started
+    with a spin ~ U(-5, 5), random actions, 24 env-steps of 50 substeps (RigidBody.cs:66-96 under maximum contact load).
+      * all 16 384 records (state, flags, step counters), observations, rewards and done flags bit-exact against the oracle
+        after every env-step's observe, with the kernel wb_env_create picks for this size;
+      * per-substep pair and joint traces (candidate, AABB, SAT result, axis index, normal, depth, contact points) bit-exact on a
+        512-walker sample (the first 64 walkers of every material, same start state and actions as in the big batch), and the
+        sample's final records equal the corresponding rows of the big batch."""
+    import workloads
+    n, per, steps = 16384, 2048, 24
+    rng = np.random.default_rng(5)
+    f0, iv0 = O.EnvBatch(n).get_state()
+    floors = workloads.contact_stress_start(n, per, f0, rng)
+    ref = O.EnvBatch(n, floor=floors)
+    env = gpu.EnvBatch(n, floor_materials=floors)
+    ref.set_state(f0, iv0)
+    env.set_state(f0, iv0)
+    sample = np.concatenate([np.arange(k * per, k * per + 64) for k in range(8)])
+    sfloors = [floors[i] for i in sample]
+    sref = O.EnvBatch(len(sample), floor=sfloors)
+    senv = gpu.EnvBatch(len(sample), floor_materials=sfloors)
+    sref.set_state(f0[sample].copy(), iv0[sample].copy())
+    senv.set_state(f0[sample].copy(), iv0[sample].copy())
+    contacts = sat = 0
+    for t in range(steps):
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        obs, rew, done = env.step(a, auto_reset=False)
+        robs, rrew, rdone = ref.step(a, auto_reset=False)
+        assert np.array_equal(obs.view(np.uint32), robs.view(np.uint32)), f"observations differ at env-step {t}"
+        assert np.array_equal(rew.view(np.uint32), rrew.view(np.uint32)) and np.array_equal(done, rdone), f"reward/done differ at env-step {t}"
+        senv.take_actions(a[sample])
+        sref.take_actions(a[sample])
+        pt, jt = senv.debug_contacts(gpu.DT_FRAME)
+        rpt, rjt = sref.step_objects(O.DT_FRAME, 50, trace=True)
+        for name in pt.dtype.names:
+            assert np.array_equal(pt[name].view(np.uint32), rpt[name].view(np.uint32)), f"pair trace field {name} differs at env-step {t}"
+        for name in jt.dtype.names:
+            assert np.array_equal(jt[name].view(np.uint32), rjt[name].view(np.uint32)), f"joint trace field {name} differs at env-step {t}"
+        contacts += int(rpt["ncontacts"].sum())
+        sat += int(rpt["sat"].sum())
+        senv.observe()
+        sref.observe()
+    assert_state_equal(env, ref, "contact stress, 16384 walkers")
+    assert_state_equal(senv, sref, "contact stress, traced sample")
+    gf, giv = env.get_state()
+    sf, siv = senv.get_state()
+    # (flags only: Environment._steps is advanced by the fused step, not by the granular TakeActions / StepObjects / observe calls)
+    assert np.array_equal(gf[sample].view(np.uint32), sf.view(np.uint32)) and np.array_equal(giv[sample][:, 0], siv[:, 0])
+    # the sweep really is contact-heavy: ~55 SAT collisions and ~65 contact points per walker per env-step
+    assert sat > 30 * len(sample) * steps and contacts > 30 * len(sample) * steps
+
+
 def test_user_material_plugin(gpu, O):
     m = gpu.IMaterial(7.5, 0.55, 0.33).register()
     assert m.id >= 8

@@ -103,7 +103,57 @@ def test_ppo_gradient_matches_oracle(gpu, O, n, batch_size, variant):
     assert skipped == rskip == 0
     assert rel_err(agent.actor.get_grads(), actor.get_grads()) < 1e-4
     assert rel_err(agent.critic.get_grads(), critic.get_grads()) < 1e-4
+    errs = per_layer_rel_err(agent.actor.get_grads(), actor.get_grads(), ACTOR_BLOCKS)
+    errs.update(per_layer_rel_err(agent.critic.get_grads(), critic.get_grads(), CRITIC_BLOCKS))
+    assert max(errs.values()) < 1e-4, errs
     assert abs(closs - rcl) <= 1e-4 * max(1.0, abs(rcl)) and abs(aloss - ral) <= 1e-4 * max(1.0, abs(ral))
+
+
+# dense layers inside the flat parameter vectors: (name, offset, count)
+ACTOR_BLOCKS = [("actor W1", 0, 768), ("actor b1", 768, 64), ("actor W2", 832, 4096), ("actor b2", 4928, 64), ("actor W3", 4992, 256),
+                ("actor b3", 5248, 4)]
+CRITIC_BLOCKS = [("critic W1", 0, 768), ("critic b1", 768, 64), ("critic W2", 832, 64), ("critic b2", 896, 1)]
+
+
+def per_layer_rel_err(got, ref, blocks):
+    """max |got - ref| of every dense layer's dW / db, normalised by THAT block's own max |ref| (a small-magnitude layer is held
+    to the same relative tolerance as the largest one)."""
+    out = {}
+    for name, off, cnt in blocks:
+        g, r = got[off:off + cnt], ref[off:off + cnt]
+        out[name] = float(np.abs(g - r).max() / (np.abs(r).max() + 1e-30))
+    return out
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ppo_gradient_matches_oracle_on_the_bench_minibatch(gpu, O, variant):
+    """BASELINE configs[2] as bench.py times it: ONE 65 536-sample minibatch drawn by the bench's own generator
+    (workloads.ppo_minibatch: full-spread observations, old log-probabilities perturbed by N(0, 0.1)), batch_size = 65 536,
+    through wb_ppo_grad against the per-sample oracle (PPOAgent.cs:218-346) -- every dense layer's dW and db within 1e-4 of the
+    oracle relative to that layer's own largest entry.  Samples that sit within rounding distance of a discontinuity of the
+    loss (clip boundary, LeakyReLU kink) are replaced first: there either branch is legitimate (see keep_clear_of_leaky_kinks)."""
+    import workloads
+    n = 65536
+    agent, actor, critic, ohp = make_pair(gpu, O, 42, n, variant=variant)
+    rng = np.random.default_rng(1234 + 1)
+    states = keep_clear_of_leaky_kinks(workloads.ppo_states(rng, n), actor.get_params(), critic.get_params())
+    states, actions, old_logp, adv, ret = workloads.ppo_minibatch(rng, n, actor.forward, states=states)
+    mean = actor.forward(states)
+    std = np.exp(np.float32(-1.0))
+    logp = (-np.log(std) - np.log(np.sqrt(2 * np.pi)) - 0.5 * ((actions - mean) / std) ** 2).astype(np.float64)
+    ratio = np.exp(logp - old_logp)
+    old_logp[(np.abs(ratio - 1.3) < 1e-3) | (np.abs(ratio - 0.7) < 1e-3)] += np.float32(0.01)
+    closs, aloss, skipped = agent.Gradients(states, actions, old_logp, adv, ret)
+    rskip, rcl, ral = O.ppo_train_batch(actor, critic, ohp, states, actions, old_logp, adv, ret, optimise=False)
+    assert skipped == rskip == 0
+    errs = per_layer_rel_err(agent.actor.get_grads(), actor.get_grads(), ACTOR_BLOCKS)
+    errs.update(per_layer_rel_err(agent.critic.get_grads(), critic.get_grads(), CRITIC_BLOCKS))
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 1e-4, f"{worst}: {errs[worst]:.3e} (all layers: {errs})"
+    assert abs(closs - rcl) <= 1e-4 * max(1.0, abs(rcl)) and abs(aloss - ral) <= 1e-4 * max(1.0, abs(ral))
+    # clipped and unclipped samples are both present in numbers: the minibatch exercises both branches of the surrogate
+    clipped = ((ratio > 1.3) | (ratio < 0.7)).mean()
+    assert 0.001 < clipped < 0.5
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -190,6 +240,19 @@ def test_weights_file_roundtrip(gpu, O):
     assert other.actor.Load(actor_lines) and other.critic.Load(critic_lines)
     assert np.array_equal(other.actor.get_flat(), agent.actor.get_flat())
     assert not other.actor.Load(critic_lines)  # structure line mismatch -> ignored like NeuralNetwork.Load
+    # a file with fewer dense lines than layers updates the leading layers only (NeuralNetwork.cs:110-113)
+    third = gpu.PPOAgent(seed=10)
+    before = third.actor.get_flat().copy()
+    assert third.actor.Load(actor_lines[:2])
+    after = third.actor.get_flat()
+    assert np.array_equal(after[:832], agent.actor.get_flat()[:832]) and np.array_equal(after[832:], before[832:])
+    # ValidateWeights: one unparsable token anywhere -> nothing is loaded (NeuralNetwork.cs:118-156)
+    bad = list(actor_lines)
+    bad[3] = bad[3].replace(" B ", " B x", 1)
+    fourth = gpu.PPOAgent(seed=11)
+    before = fourth.actor.get_flat().copy()
+    assert not fourth.actor.Load(bad) and np.array_equal(fourth.actor.get_flat(), before)
+    assert not fourth.actor.Load(actor_lines + [actor_lines[1]])  # more lines than layers (the reference throws)
 
 
 def test_unsupported_topology_fails_loudly(gpu):
