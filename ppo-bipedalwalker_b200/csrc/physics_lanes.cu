@@ -33,10 +33,28 @@
 #include "physics.cuh"
 #include "physics_math.cuh"
 
+// unroll factor of the vote-free SAT rounds (experiments: -DWB_SAT_UNROLL=1 keeps the loops rolled -> smaller code)
+#ifndef WB_SAT_UNROLL
+#define WB_SAT_UNROLL 6
+#endif
+
 namespace wb {
 namespace pl {
+constexpr int kSatUnroll = WB_SAT_UNROLL;
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+
+#ifdef WB_PHASE_PROFILE
+// experiment builds only (scripts/build_variant.sh prof -DWB_PHASE_PROFILE): cycle accounting of the compacting kernel
+__device__ unsigned long long g_prof[24];
+__device__ __forceinline__ long long prof_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+__device__ long long g_prof_sat_scratch;  // (unused; keeps the symbol table stable)
+#endif
+
 
 __constant__ Material c_materials[WB_MAX_MATERIALS];
 __constant__ float c_init_state[kStateFloats];  // state record of a freshly created walker
@@ -390,23 +408,29 @@ __device__ __forceinline__ bool aabb_hit(float2 amin, float2 amax, float2 bmin, 
 // `want`: this env takes part (candidate exists at this position of its list order).
 // `sep_axis` (may be null): receives the index (0..11, A's edges then B's) of the first separating axis this lane found
 // VOTE: 1 = one vote per SAT round with an early stop, 0 = straight-line rounds and one vote at the end, -1 = by layout (see kVote)
-template <class EV, int G, bool TRACE, bool FLOORB, int VOTE = -1>
+// KNOWN_HIT: the caller has already established that the bounding boxes overlap (stage 1 of the compacting kernel)
+template <class EV, int G, bool TRACE, bool FLOORB, int VOTE = -1, bool KNOWN_HIT = false>
 __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_pair_trace* tr, int* sep_axis = nullptr) {
   const FloorConst& fl = *e.fl;
   float2 PA[6], PB[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) PA[i] = V2(e, A * 6 + i);
-  float2 amin, amax, bmin, bmax;
-  aabb6(PA, amin, amax);
-  if (FLOORB) {
-    bmin = fl.bb_min;
-    bmax = fl.bb_max;
-  } else {
+  if (!FLOORB) {
 #pragma unroll
     for (int i = 0; i < 6; i++) PB[i] = V2(e, B * 6 + i);
-    aabb6(PB, bmin, bmax);
   }
-  const bool hit = want && aabb_hit(amin, amax, bmin, bmax);
+  bool hit = want;
+  if (!KNOWN_HIT) {
+    float2 amin, amax, bmin, bmax;
+    aabb6(PA, amin, amax);
+    if (FLOORB) {
+      bmin = fl.bb_min;
+      bmax = fl.bb_max;
+    } else {
+      aabb6(PB, bmin, bmax);
+    }
+    hit = want && aabb_hit(amin, amax, bmin, bmax);
+  }
   if (FLOORB && hit) e.flags |= (1 << A);  // if (body._isFloor) Collided = true  (before SAT: RigidBody.cs:75)
   wb_pair_trace rec;
   if (TRACE) {
@@ -418,6 +442,10 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
     rec.ncontacts = 0;
     rec.c0x = rec.c0y = rec.c1x = rec.c1y = 0.0f;
   }
+#ifdef WB_PHASE_PROFILE
+  const long long rp_t0 = prof_clock();
+  long long rp_t1 = rp_t0;
+#endif
   bool colliding = false;
   if (__any_sync(kFull, hit)) {
     // AxisChecks(A, B) then AxisChecks(B, A) (SATCollision.cs:19-29,39-59): axis i of the 12 (10 against the floor) goes to
@@ -465,11 +493,20 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
       skip = (axis.x == 0.0f) && (axis.y == 0.0f);
       return vnormalize_fast(axis);
     };
+    // the same from the registers that already hold both polygons (two lanes per pair: lane parity picks between two static
+    // edges, so no shared-memory access with a runtime index is needed); r is a compile-time round index
+    auto edge_axis_reg = [&](const float2 (&P)[6], int r, bool odd, bool& skip) {
+      const float2 p0 = odd ? P[(r + 1) % 6] : P[r % 6], p1 = odd ? P[(r + 2) % 6] : P[(r + 1) % 6];
+      const float2 edge = vsub(p1, p0);
+      const float2 axis = mk2(-edge.y, edge.x);
+      skip = (axis.x == 0.0f) && (axis.y == 0.0f);
+      return vnormalize_fast(axis);
+    };
     auto round_a_vs_floor = [&](int r) {  // AxisChecks(A, floor): A's 6 edges
       const int i = r + e.gsub;
       const bool valid = i < 6;
       bool skip;
-      const float2 axis = edge_axis(A, valid ? i : 0, skip);
+      const float2 axis = (G == 2 && !kVote) ? edge_axis_reg(PA, r, e.gsub != 0, skip) : edge_axis(A, valid ? i : 0, skip);
       float omin, omax, tmin, tmax;
       project6(PA, axis, omin, omax);
       project4(fl.v, axis, tmin, tmax);
@@ -490,7 +527,12 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
       const bool ownA = i < 6;
       const int k = ownA ? i : (valid ? i - 6 : 0);
       bool skip;
-      const float2 axis = edge_axis(ownA ? A : B, k, skip);
+      float2 axis;
+      if (G == 2 && !kVote) {  // (r is even and known at compile time after unrolling: r < 6 <=> the edge belongs to A)
+        axis = (r < 6) ? edge_axis_reg(PA, r, e.gsub != 0, skip) : edge_axis_reg(PB, r - 6, e.gsub != 0, skip);
+      } else {
+        axis = edge_axis(ownA ? A : B, k, skip);
+      }
       float amn, amx, bmn, bmx;
       project6(PA, axis, amn, amx);
       project6(PB, axis, bmn, bmx);
@@ -510,17 +552,20 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
       }
     } else {
       if (FLOORB) {
-#pragma unroll
+#pragma unroll kSatUnroll
         for (int r = 0; r < 6; r += G) round_a_vs_floor(r);
-#pragma unroll
+#pragma unroll kSatUnroll
         for (int r = 0; r < 4; r += G) round_floor_vs_a(r);
       } else {
-#pragma unroll
+#pragma unroll kSatUnroll
         for (int r = 0; r < 12; r += G) round_pole(r);
       }
       sep = group_any<EV, G>(e, my_sep);
     }
     colliding = hit && !sep;
+#ifdef WB_PHASE_PROFILE
+    rp_t1 = prof_clock();
+#endif
     if (__any_sync(kFull, colliding)) {
       if (G > 1) {
 #pragma unroll
@@ -627,7 +672,19 @@ __device__ __forceinline__ void resolve_pair(EV& e, bool want, int A, int B, wb_
   if (TRACE) {
     if (tr && want && e.gsub == 0) *tr = rec;
   }
+#ifdef WB_PHASE_PROFILE
+  const unsigned prof_want = __ballot_sync(kFull, want), prof_coll = __ballot_sync(kFull, colliding);
+  if (!TRACE && (threadIdx.x & 31) == 0) {
+    const long long rp_t2 = prof_clock();
+    const int k = FLOORB ? 1 : 0;
+    atomicAdd(&g_prof[8 + 4 * k + 0], (unsigned long long)(rp_t1 - rp_t0));   // AABB + SAT
+    atomicAdd(&g_prof[8 + 4 * k + 1], (unsigned long long)(rp_t2 - rp_t1));   // contact pipeline + moves + impulses
+    atomicAdd(&g_prof[8 + 4 * k + 2], 1ull);                                  // warp-level calls
+    atomicAdd(&g_prof[8 + 4 * k + 3], (unsigned long long)__popc(prof_want) | ((unsigned long long)__popc(prof_coll) << 32));
+  }
+#endif
 }
+
 
 // ---------------------------------------------------------------- RigidBody.Step, RigidBody.cs:54-61,116-140
 // `on`: this lane group really steps body b (false for the right-leg half while the left-leg half steps the Body)
@@ -960,6 +1017,16 @@ static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t str
 namespace pc {
 using namespace pl;
 
+// -DWB_PHASE_PROFILE (experiment builds only, scripts/build_variant.sh): cycles per warp spent in stage 1, at the barrier before
+// the drain, in the drain and at the barrier after it, summed over all warps of all CTAs; read with wb_prof_read (below)
+#ifdef WB_PHASE_PROFILE
+#define WB_PROF_DECL long long prof_t = prof_clock(); unsigned long long prof_acc[4] = {0, 0, 0, 0}; unsigned long long prof_items = 0, prof_rounds = 0
+#define WB_PROF_MARK(k) do { const long long now_ = prof_clock(); prof_acc[k] += (unsigned long long)(now_ - prof_t); prof_t = now_; } while (0)
+#else
+#define WB_PROF_DECL
+#define WB_PROF_MARK(k)
+#endif
+
 // kE walkers (= threads) share one queue and advance in lockstep.  Measured at 262144 walkers (ms per env-step): kE = 32 (ONE
 // WARP per CTA, rounds separated by __syncwarp only, no block barrier anywhere) 8.86 -- sparse per-warp queues execute the
 // expensive stage once per warp however few items it has; 64: 7.35; 128: 5.93; 256: 5.45 (default; 4.79 today); 512: 6.06 (one CTA
@@ -975,6 +1042,9 @@ struct Shared {
   unsigned char axis[4 * kE];   // last separating axis per ordered leg pair {LLL->LLU, LLU->LLL, RLL->RLU, RLU->RLL}
   unsigned short queue[3 * kE];  // a floor round holds at most three items per walker (two leg segments + the Body)
   int count[2];  // ping-pong: the counter of the next round is cleared while the current one drains
+#ifdef WB_PHASE_PROFILE
+  long long prof_arrive[2][2][32];  // [round parity][barrier][warp]: arrival time at the barrier
+#endif
 };
 // The noinline stages below rebuild their shared-memory pointers from this array instead of receiving pointers as arguments:
 // an argument is a generic 64-bit address (LD / ST through the generic path), a pointer derived here stays LDS / STS.
@@ -1138,11 +1208,11 @@ __device__ __noinline__ void drain(int parity) {
     group_env_for_column(q, S, col, valid);
     if (KIND == kItemPole) {
       int sep_axis = -1;
-      resolve_pair<EVG, kG, false, false, kDrainVote>(q, valid, payload, partner_of(payload), nullptr, &sep_axis);
+      resolve_pair<EVG, kG, false, false, kDrainVote, true>(q, valid, payload, partner_of(payload), nullptr, &sep_axis);
       // the lane that saw the lowest separating axis of the group records it (any separating axis is a valid cache entry)
       if (valid && sep_axis >= 0) S.axis[pair_slot(payload) * kE + col] = (unsigned char)sep_axis;
     } else if (KIND == kItemFloor) {
-      resolve_pair<EVG, kG, false, true, kDrainVote>(q, valid, payload, FLOOR, nullptr);
+      resolve_pair<EVG, kG, false, true, kDrainVote, true>(q, valid, payload, FLOOR, nullptr);
     } else {
       const int k = payload;
       const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
@@ -1152,7 +1222,7 @@ __device__ __noinline__ void drain(int parity) {
 }
 
 template <int kE>
-__global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const PhysicsParams p) {
+__global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)) physics_compact_kernel(const PhysicsParams p) {
   using EV = Env<1, kE>;
   Shared<kE>& S = shm<kE>();
   const int tid = threadIdx.x;
@@ -1245,11 +1315,38 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
     };
     // one queue round: (stage 1 already pushed) barrier, drain, barrier; the other counter is cleared in between
     int parity = 0;
+    WB_PROF_DECL;
+    // (the clock read after a BAR.SYNC.DEFER_BLOCKING can issue before the warp really blocks, so waits are not measured around
+    //  the barrier: every warp publishes its ARRIVAL time and afterwards charges (latest arrival - own arrival) as its wait)
     auto round = [&](auto drain_fn) {
+#ifdef WB_PHASE_PROFILE
+      const int pw = tid >> 5, nw = kE >> 5;
+      long long t_arr0 = prof_clock();
+      if ((tid & 31) == 0) S.prof_arrive[parity][0][pw] = t_arr0;
+#endif
       scope_sync<kE>();
+#ifdef WB_PHASE_PROFILE
+      long long last0 = 0;
+      for (int w = 0; w < nw; w++) last0 = max(last0, S.prof_arrive[parity][0][w]);
+      prof_acc[0] += (unsigned long long)(t_arr0 - prof_t);  // stage 1: from the end of the previous round to my arrival
+      prof_acc[1] += (unsigned long long)(last0 - t_arr0);   // wait before the drain
+      prof_items += S.count[parity];
+      prof_rounds++;
+#endif
       if (tid == 0) S.count[parity ^ 1] = 0;
       drain_fn();
+#ifdef WB_PHASE_PROFILE
+      long long t_arr1 = prof_clock();
+      if ((tid & 31) == 0) S.prof_arrive[parity][1][pw] = t_arr1;
+#endif
       scope_sync<kE>();
+#ifdef WB_PHASE_PROFILE
+      long long last1 = 0;
+      for (int w = 0; w < nw; w++) last1 = max(last1, S.prof_arrive[parity][1][w]);
+      prof_acc[2] += (unsigned long long)(t_arr1 - last0);  // drain: from the release of the first barrier to my arrival
+      prof_acc[3] += (unsigned long long)(last1 - t_arr1);  // wait after the drain
+      prof_t = last1;
+#endif
       parity ^= 1;
     };
 
@@ -1306,6 +1403,16 @@ __global__ void __launch_bounds__(kE, 512 / kE) physics_compact_kernel(const Phy
         }
       }
     }
+#ifdef WB_PHASE_PROFILE
+    if ((tid & 31) == 0) {
+      for (int k = 0; k < 4; k++) atomicAdd(&g_prof[k], prof_acc[k]);
+      atomicAdd(&g_prof[4], 1ull);
+      if (tid == 0) {
+        atomicAdd(&g_prof[5], prof_items);
+        atomicAdd(&g_prof[6], prof_rounds);
+      }
+    }
+#endif
   }
 
   if (p.phases & kPhaseObserve) {
@@ -1378,7 +1485,17 @@ static cudaError_t launch_compact(const PhysicsParams& p, cudaStream_t stream) {
 
 }  // namespace pc
 
-
+#ifdef WB_PHASE_PROFILE
+extern "C" int wb_prof_read(unsigned long long* out24, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out24, pl::g_prof, sizeof(unsigned long long) * 24) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[24] = {};
+    cudaMemcpyToSymbol(pl::g_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 // ---------------------------------------------------------------- host side
 cudaError_t upload_materials(const Material* table, int count) {
@@ -1397,7 +1514,7 @@ cudaError_t upload_scene_constants(const float* init_state92, const FloorConst* 
 // of 128 walkers, kept for comparison)
 bool physics_lanes_supported(int variant) {
   switch (variant) {
-    case 1: case 2: case 4: case 8: case 16: case 32: case 104: case 108: case 116: case 1001: case 1002: case 1003: return true;
+    case 1: case 2: case 4: case 8: case 16: case 32: case 104: case 108: case 116: case 1001: case 1002: case 1003: case 1004: case 1005: return true;
     default: return false;
   }
 }
@@ -1417,6 +1534,8 @@ cudaError_t launch_physics(const PhysicsParams& p, int variant, bool trace, cuda
     case 1001: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<256>(p, stream);
     case 1002: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<32>(p, stream);
     case 1003: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<128>(p, stream);
+    case 1004: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<192>(p, stream);
+    case 1005: return trace ? pl::launch_l<1, 1>(p, true, stream) : pc::launch_compact<160>(p, stream);
     default: return cudaErrorInvalidValue;
   }
 }
