@@ -27,8 +27,9 @@
  *   f[88..91] Joint._currentTorque                                               (Joint.cs:18)
  *   i[0] flags: bit0-4 Collided(LLL,LLU,Body,RLL,RLU) bit5 Walker.Terminal bit6 floor-first list order
  *   i[1] Environment._steps
- * On the device the state is a structure of arrays: float state[92][N], int32 flags[N], int32 steps[N].
- * wb_env_{get,set}_state use that same SoA layout on the host side ([92][N] floats, [2][N] ints).
+ * wb_env_{get,set}_state exchange the records as structure-of-arrays blobs on the host side ([92][N] floats, [2][N] ints).
+ * On the device the state is also a structure of arrays over walkers, with the x and y of a point adjacent (float2 rows for
+ * vertices / centroids / velocities, float rows for the rest; csrc/physics.cuh) -- the library converts.
  */
 #ifndef WALKER_B200_H
 #define WALKER_B200_H

@@ -170,7 +170,7 @@ struct wb_env_batch {
   int lanes = 0;  // kernel variant: lanes per environment (1, 2, 4, 8, 16) or 1001 (compacting); chosen from the batch size at creation
   int64_t launches = 0;
   // device state (structure of arrays)
-  float* d_state = nullptr;    // [92][n_pad]
+  float* d_state = nullptr;    // 92 floats per walker in the device layout of physics.cuh (state_index), rows padded to n_pad
   int32_t* d_flags = nullptr;  // [n_pad]
   int32_t* d_steps = nullptr;  // [n_pad]
   float* d_pos = nullptr;      // [2][n_pad]
@@ -243,7 +243,7 @@ int32_t wb_material_get(int32_t id, float* inverse_mass, float* restitution, flo
 }
 
 static int32_t launch(wb_env_batch* env, int phases, float dt, const float* d_actions, float* d_obs, float* d_reward,
-                      uint8_t* d_done, const uint8_t* d_mask, wb_pair_trace* d_pt, wb_joint_trace* d_jt) {
+                      uint8_t* d_done, const uint8_t* d_mask, wb_pair_trace* d_pt, wb_joint_trace* d_jt, int n_override = 0) {
   PhysicsParams p{};
   p.state = env->d_state;
   p.flags = env->d_flags;
@@ -259,7 +259,7 @@ static int32_t launch(wb_env_batch* env, int phases, float dt, const float* d_ac
   p.done = d_done;
   p.pair_trace = d_pt;
   p.joint_trace = d_jt;
-  p.n = env->n;
+  p.n = n_override > 0 ? n_override : env->n;
   p.n_pad = env->n_pad;
   p.dt = dt;
   p.iterations = env->hp.iterations;
@@ -337,8 +337,11 @@ int32_t wb_env_create(int32_t n_envs, const uint8_t* floor_material_ids, const u
   WB_ENV_TRY(cudaMemset(env->d_pos, 0, sizeof(float) * 2 * np));
   WB_ENV_TRY(cudaMemcpy(env->d_floor_mat, fm.data(), np, cudaMemcpyHostToDevice));
   WB_ENV_TRY(cudaMemcpy(env->d_walker_mat, wm.data(), np, cudaMemcpyHostToDevice));
-  // constructor state: walker first, floor last (Environment.cs:46-48), then InitialState
-  if (int32_t rc = launch(env, kPhaseResetMasked | kPhaseFirstEpisode, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) {
+  // constructor state: walker first, floor last (Environment.cs:46-48), then InitialState -- for the padding of the rows too:
+  // the pad walkers are real, idle walkers (they never receive actions and are never read), so a lockstep CTA of the compacting
+  // kernel can always move whole row segments
+  if (int32_t rc = launch(env, kPhaseResetMasked | kPhaseFirstEpisode, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          env->n_pad)) {
     wb_env_destroy(env);
     return rc;
   }
@@ -418,25 +421,57 @@ int32_t wb_env_reset(wb_env_batch* env, const uint8_t* mask_host, int32_t first_
   return WB_OK;
 }
 
+// canonical host blob [92][n] <-> the device layout (physics.cuh: state_index); also fills Walker._position on the way in
+__global__ void state_layout_kernel(float* __restrict__ canonical, float* __restrict__ dev_state, float* __restrict__ pos, int n, int n_pad,
+                                    int to_device) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)kStateFloats * n) return;
+  const int f = (int)(i / n);
+  const size_t env = i % n;
+  if (to_device) {
+    const float v = canonical[i];
+    dev_state[state_index(f, env, n_pad)] = v;
+    // Walker._position == Body centroid at every step boundary (Walker.cs:52): floats 62 / 63 of the record
+    if (f == 62) pos[env] = v;
+    if (f == 63) pos[n_pad + env] = v;
+  } else {
+    canonical[i] = dev_state[state_index(f, env, n_pad)];
+  }
+}
+
+static int32_t convert_state(wb_env_batch* env, float* host_blob, bool to_device) {
+  const size_t n = env->n, bytes = sizeof(float) * kStateFloats * n;
+  float* d_tmp = nullptr;
+  WB_CUDA(cudaMalloc(&d_tmp, bytes));
+  cudaError_t e = cudaSuccess;
+  if (to_device) e = cudaMemcpyAsync(d_tmp, host_blob, bytes, cudaMemcpyHostToDevice, env->stream);
+  if (e == cudaSuccess) {
+    const size_t total = (size_t)kStateFloats * n;
+    state_layout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, env->stream>>>(d_tmp, env->d_state, env->d_pos, (int)n, env->n_pad,
+                                                                                 to_device ? 1 : 0);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && !to_device) e = cudaMemcpyAsync(host_blob, d_tmp, bytes, cudaMemcpyDeviceToHost, env->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(env->stream);
+  cudaFree(d_tmp);
+  if (e != cudaSuccess) return fail(WB_ERR_CUDA, "state layout conversion: %s", cudaGetErrorString(e));
+  return WB_OK;
+}
+
 int32_t wb_env_set_state(wb_env_batch* env, const float* state_f_host, const int32_t* state_i_host) {
   WB_REQUIRE(env && state_f_host && state_i_host, "null argument");
-  const size_t n = env->n, np = env->n_pad;
-  WB_CUDA(cudaMemcpy2DAsync(env->d_state, np * sizeof(float), state_f_host, n * sizeof(float), n * sizeof(float), kStateFloats,
-                            cudaMemcpyHostToDevice, env->stream));
+  const size_t n = env->n;
+  if (int32_t rc = convert_state(env, const_cast<float*>(state_f_host), true)) return rc;
   WB_CUDA(cudaMemcpyAsync(env->d_flags, state_i_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, env->stream));
   WB_CUDA(cudaMemcpyAsync(env->d_steps, state_i_host + n, n * sizeof(int32_t), cudaMemcpyHostToDevice, env->stream));
-  // Walker._position == Body centroid at every step boundary (Walker.cs:52): rows 62/63 of the record
-  WB_CUDA(cudaMemcpyAsync(env->d_pos, env->d_state + 62 * np, np * sizeof(float), cudaMemcpyDeviceToDevice, env->stream));
-  WB_CUDA(cudaMemcpyAsync(env->d_pos + np, env->d_state + 63 * np, np * sizeof(float), cudaMemcpyDeviceToDevice, env->stream));
   WB_CUDA(cudaStreamSynchronize(env->stream));
   return WB_OK;
 }
 
 int32_t wb_env_get_state(wb_env_batch* env, float* state_f_host, int32_t* state_i_host) {
   WB_REQUIRE(env && state_f_host && state_i_host, "null argument");
-  const size_t n = env->n, np = env->n_pad;
-  WB_CUDA(cudaMemcpy2DAsync(state_f_host, n * sizeof(float), env->d_state, np * sizeof(float), n * sizeof(float), kStateFloats,
-                            cudaMemcpyDeviceToHost, env->stream));
+  const size_t n = env->n;
+  if (int32_t rc = convert_state(env, state_f_host, false)) return rc;
   WB_CUDA(cudaMemcpyAsync(state_i_host, env->d_flags, n * sizeof(int32_t), cudaMemcpyDeviceToHost, env->stream));
   WB_CUDA(cudaMemcpyAsync(state_i_host + n, env->d_steps, n * sizeof(int32_t), cudaMemcpyDeviceToHost, env->stream));
   WB_CUDA(cudaStreamSynchronize(env->stream));

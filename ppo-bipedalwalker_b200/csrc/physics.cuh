@@ -7,8 +7,19 @@
 
 namespace wb {
 
-constexpr int kEnvPad = 8;        // the SoA rows are padded to a multiple of 8 environments (32-byte sectors)
+constexpr int kEnvPad = 256;      // the SoA rows are padded to a multiple of 256 environments: one lockstep CTA of the compacting
+                                  // kernel always moves whole 2 KB / 1 KB row segments with bulk copies (pad walkers are real, idle walkers)
 constexpr int kStateFloats = WB_STATE_FLOATS;
+
+// Device layout of the state record (structure of arrays over walkers, x/y of one point adjacent):
+//   float2 slot s = 0..38 (29 vertices, 5 cached centroids, 5 linear velocities = record floats 2s, 2s+1):  state2[s][n_pad]
+//   float rows 78..91 (angular velocities, tracked angles, joint torques):                                state[f][n_pad]
+// A walker's (x, y) pairs sit next to each other, so a row segment of a CTA's walkers lands in the kernels' shared-memory
+// columns ([slot][walker] float2) with ONE contiguous copy -- cp.async.bulk in the compacting kernel.
+__host__ __device__ inline size_t state_index(int f, size_t env, size_t n_pad) {
+  return f < 78 ? ((size_t)(f >> 1) * n_pad + env) * 2 + (size_t)(f & 1) : (size_t)f * n_pad + env;
+}
+constexpr int kStateSlots2 = 39;  // float2 slots of the record
 
 struct Material {
   float inverse_mass, restitution, friction;
@@ -27,7 +38,7 @@ enum : int {
 };
 
 struct PhysicsParams {
-  float* state;        // [92][n_pad]
+  float* state;        // the record in the device layout above (state_index)
   int32_t* flags;      // [n_pad]
   int32_t* steps;      // [n_pad]
   float* pos;          // [2][n_pad]  Walker._position (Walker.cs:19)

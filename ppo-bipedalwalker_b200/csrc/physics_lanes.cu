@@ -780,10 +780,19 @@ __global__ void __launch_bounds__(32, (L <= 4) ? 16 : 8) physics_lanes_kernel(co
   // ---- stage the E records (all 32 lanes share the loads: SoA rows are contiguous over envs) and the floor constants
   for (int w = lane; w < (int)(sizeof(FloorConst) / 4); w += 32)
     reinterpret_cast<uint32_t*>(&s_floor)[w] = reinterpret_cast<const uint32_t*>(&c_floor)[w];
+  // (x, y) of a point are adjacent in HBM: the E walkers' share of a float2 slot is one run of 2E floats
   for (int idx = lane; idx < 88 * E; idx += 32) {
-    const int f = idx / E, c = idx % E;
+    int f, c;
+    if (idx < 78 * E) {
+      const int slot = idx / (2 * E), r = idx % (2 * E);
+      c = r >> 1;
+      f = 2 * slot + (r & 1);
+    } else {
+      f = 78 + (idx - 78 * E) / E;
+      c = idx % E;
+    }
     const int env = env0 + c;
-    const float v = (env < p.n) ? p.state[(size_t)f * p.n_pad + env] : c_init_state[f];
+    const float v = (env < p.n) ? p.state[state_index(f, env, p.n_pad)] : c_init_state[f];
     s_state[record_word<E>(f) + (f < 78 ? 2 * c : c)] = v;
   }
   __syncwarp();
@@ -940,8 +949,16 @@ __global__ void __launch_bounds__(32, (L <= 4) ? 16 : 8) physics_lanes_kernel(co
   __syncwarp();
   // ---- write the records back (same coalesced pattern)
   for (int idx = lane; idx < 88 * E; idx += 32) {
-    const int f = idx / E, c = idx % E;
-    if (env0 + c < p.n) p.state[(size_t)f * p.n_pad + env0 + c] = s_state[record_word<E>(f) + (f < 78 ? 2 * c : c)];
+    int f, c;
+    if (idx < 78 * E) {
+      const int slot = idx / (2 * E), r = idx % (2 * E);
+      c = r >> 1;
+      f = 2 * slot + (r & 1);
+    } else {
+      f = 78 + (idx - 78 * E) / E;
+      c = idx % E;
+    }
+    if (env0 + c < p.n) p.state[state_index(f, env0 + c, p.n_pad)] = s_state[record_word<E>(f) + (f < 78 ? 2 * c : c)];
   }
 }
 
@@ -1014,6 +1031,45 @@ static cudaError_t launch_l(const PhysicsParams& p, bool trace, cudaStream_t str
 // Left and right leg are swept in the same phase (they share no mutable state, see the leg split above), which halves the
 // number of barriers and doubles the queue density.  Arithmetic and order per walker are those of the plain kernel: the
 // results are bit-identical (tests/test_physics_gpu.py runs every variant against the oracle).
+// ---- cp.async.bulk (the TMA engine's 1-D form): contiguous global <-> shared copies issued by one thread
+namespace bulk {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void load(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void commit_and_wait_reads() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+}  // namespace bulk
+
 namespace pc {
 using namespace pl;
 
@@ -1042,6 +1098,7 @@ struct Shared {
   unsigned char axis[4 * kE];   // last separating axis per ordered leg pair {LLL->LLU, LLU->LLL, RLL->RLU, RLU->RLL}
   unsigned short queue[3 * kE];  // a floor round holds at most three items per walker (two leg segments + the Body)
   int count[2];  // ping-pong: the counter of the next round is cleared while the current one drains
+  unsigned long long stage_bar;  // mbarrier of the bulk-copy staging
 #ifdef WB_PHASE_PROFILE
   long long prof_arrive[2][2][32];  // [round parity][barrier][warp]: arrival time at the barrier
 #endif
@@ -1233,17 +1290,31 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
 
   for (int w = tid; w < (int)(sizeof(FloorConst) / 4); w += kE)
     reinterpret_cast<uint32_t*>(&S.floor)[w] = reinterpret_cast<const uint32_t*>(&c_floor)[w];
-  // stage the record of my walker (SoA rows are contiguous over walkers: coalesced); 22 independent loads in flight per thread
-#pragma unroll 1
-  for (int f0 = 0; f0 < 88; f0 += 22) {
-    float r[22];
-#pragma unroll
-    for (int j = 0; j < 22; j++) r[j] = p.state[(size_t)(f0 + j) * p.n_pad + envc];
-#pragma unroll
-    for (int j = 0; j < 22; j++) {
-      const int f = f0 + j;
-      S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = live ? r[j] : c_init_state[f];
+  // stage the CTA's records: every float2 slot of the device layout is ONE contiguous run of kE * 8 bytes (every float row kE * 4)
+  // that lands in its shared-memory column as it is -- 49 bulk copies (cp.async.bulk, completion counted on an mbarrier) issued by
+  // one thread, no register staging.  The rows are padded to whole CTAs (kEnvPad), so the runs are always complete.
+  constexpr bool kBulk = (kE % 32 == 0) && (kEnvPad % kE == 0);
+  if (kBulk) {
+    if (tid == 0) {
+      bulk::mbar_init(&S.stage_bar, 1);
+      bulk::fence_mbar_init();
     }
+    scope_sync<kE>();
+    if (tid == 0) {
+      bulk::mbar_expect_tx(&S.stage_bar, (uint32_t)(kStateSlots2 * kE * 8 + 10 * kE * 4));
+#pragma unroll 1
+      for (int s2 = 0; s2 < kStateSlots2; s2++) {  // record slot -> column slot (the Body's mirror slot, then centroids / velocities)
+        const int col_slot = s2 < 17 ? s2 : (s2 < 29 ? s2 + 1 : (s2 < 34 ? kV2Cen + (s2 - 29) : kV2Vel + (s2 - 34)));
+        bulk::load(S.state + (size_t)col_slot * kE * 2, p.state + ((size_t)s2 * p.n_pad + env0) * 2, kE * 8, &S.stage_bar);
+      }
+#pragma unroll 1
+      for (int r = 0; r < 10; r++)
+        bulk::load(S.state + (size_t)kV2Count * kE * 2 + (size_t)r * kE, p.state + (size_t)(78 + r) * p.n_pad + env0, kE * 4, &S.stage_bar);
+    }
+  } else {
+#pragma unroll 1
+    for (int f = 0; f < 88; f++)
+      S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)] = live ? p.state[state_index(f, envc, p.n_pad)] : c_init_state[f];
   }
   for (int w = tid; w < (int)(sizeof(Material) * WB_MAX_MATERIALS / 4); w += kE)
     reinterpret_cast<uint32_t*>(S.mtab)[w] = reinterpret_cast<const uint32_t*>(c_materials)[w];
@@ -1258,6 +1329,7 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
     }
   }
   if (tid == 0) S.count[0] = S.count[1] = 0;
+  if (kBulk) bulk::mbar_wait(&S.stage_bar, 0);  // the bulk copies have landed (the async proxy's writes are visible after the wait)
   scope_sync<kE>();  // the floor constants / counters written above are read by every thread of the scope
   EV e;
   env_for_column(e, S, tid, live);
@@ -1456,8 +1528,27 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
     if (p.axis_cache != nullptr)
       p.axis_cache[env] = (uint32_t)S.axis[tid] | ((uint32_t)S.axis[kE + tid] << 8) | ((uint32_t)S.axis[2 * kE + tid] << 16) |
                           ((uint32_t)S.axis[3 * kE + tid] << 24);
+    if (!kBulk) {
 #pragma unroll 8
-    for (int f = 0; f < 88; f++) p.state[(size_t)f * p.n_pad + env] = S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)];
+      for (int f = 0; f < 88; f++) p.state[state_index(f, env, p.n_pad)] = S.state[record_word<kE>(f) + (f < 78 ? 2 * tid : tid)];
+    }
+  }
+  if (kBulk) {
+    // write the records back the way they came: bulk stores shared -> global (the pad walkers of a ragged last CTA are real
+    // walkers in the padding of the rows; they never receive actions and are never read)
+    bulk::fence_proxy_async();  // this thread's generic-proxy writes to the columns -> visible to the async proxy
+    scope_sync<kE>();
+    if (tid == 0) {
+#pragma unroll 1
+      for (int s2 = 0; s2 < kStateSlots2; s2++) {
+        const int col_slot = s2 < 17 ? s2 : (s2 < 29 ? s2 + 1 : (s2 < 34 ? kV2Cen + (s2 - 29) : kV2Vel + (s2 - 34)));
+        bulk::store(p.state + ((size_t)s2 * p.n_pad + env0) * 2, S.state + (size_t)col_slot * kE * 2, kE * 8);
+      }
+#pragma unroll 1
+      for (int r = 0; r < 10; r++)
+        bulk::store(p.state + (size_t)(78 + r) * p.n_pad + env0, S.state + (size_t)kV2Count * kE * 2 + (size_t)r * kE, kE * 4);
+      bulk::commit_and_wait_reads();  // shared memory must outlive the reads of the bulk stores
+    }
   }
 }
 
