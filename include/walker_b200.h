@@ -202,7 +202,11 @@ int32_t wb_scene_step_objects(wb_scene* scene, float delta_time);
 /* layer kinds of the network DSL (PPOAgent.ParseLayers, PPOAgent.cs:96-143) */
 enum { WB_DENSE = 0, WB_RELU = 1, WB_LEAKYRELU = 2, WB_TANH = 3 };
 
-/* new PPOAgent(stateSize, actionSize) (PPOAgent.cs:23-37) with already-parsed layer lists.
+/* new PPOAgent(stateSize, actionSize) (PPOAgent.cs:23-37) with already-parsed layer lists (kinds[i] / sizes[i]; size is read
+ * for WB_DENSE only).  Any network the DSL describes is accepted within: 1..16 layers per network, state size and dense widths
+ * 1..128, action size 1..64, actor output == action_size, critic output == 1 (PPOAgent.cs:78-92), at most 32 dense layers in
+ * total; anything else fails with WB_ERR_UNSUPPORTED / WB_ERR_INVALID -- never a fallback.  The reference's default networks
+ * (Hyperparameters.cs:91-92) run on the tensor-core kernel, every other network on the any-topology kernel.
  * Weights start at zero: load them with wb_policy_set_weights (Xavier init is host-side, Matrix.cs:59-80). */
 int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t* actor_kinds, const int32_t* actor_sizes,
                          int32_t actor_layers, const int32_t* critic_kinds, const int32_t* critic_sizes, int32_t critic_layers,
@@ -210,7 +214,8 @@ int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t*
 int32_t wb_policy_destroy(wb_policy* p);
 int32_t wb_policy_set_stream(wb_policy* p, void* cuda_stream);
 int32_t wb_policy_sync(wb_policy* p);
-/* kernel variant of the MLP path: 0 = tcgen05 tensor-core kernel with 3xTF32 operands (default), 1 = fp32 CUDA-core kernel */
+/* kernel variant of the MLP path: 0 = tcgen05 tensor-core kernel with 3xTF32 operands (default networks; the default),
+ * 1 = fp32 CUDA-core kernel (default networks), 2 = the any-topology kernel (what non-default networks always use) */
 int32_t wb_policy_set_variant(wb_policy* p, int32_t variant);
 int32_t wb_policy_set_hyperparams(wb_policy* p, const wb_hyperparams* hp);
 /* flat parameter vectors, per dense layer W[out][in] row-major then b[out] (DenseLayer.Save, DenseLayer.cs:73-79). which: 0 actor, 1 critic */

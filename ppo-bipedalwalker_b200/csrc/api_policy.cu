@@ -14,13 +14,18 @@ struct wb_policy {
   cudaStream_t stream = nullptr;
   wb_hyperparams hp{};
   int64_t launches = 0;
-  int variant = 0;  // 0: tcgen05 tensor-core kernel (default), 1: fp32 CUDA-core kernel
-  int32_t iterations[5] = {0, 0, 0, 0, 0};  // DenseLayer._iteration: actor L1..L3, critic L1..L2
-  float* d_params = nullptr;    // [6149] actor | critic
-  float* d_grads = nullptr;     // [kGradFloats]
+  int variant = 0;  // 0: tcgen05 tensor-core kernel (default), 1: fp32 CUDA-core kernel, 2: the any-topology kernel (mlp_generic.cu)
+  bool default_topology = true;  // the reference's default networks: the specialised kernels apply
+  GenNet actor{}, critic{};      // both networks as parsed layer tables
+  int n_actor = kActorParams, n_critic = kCriticParams, n_total = kTotalParams;
+  int grad_floats = kGradFloats;  // n_total + {sum g_V, sum mean_k g_mu, skipped}, padded to a float4 multiple
+  int gen_ts = 0;                 // samples per tile of the generic kernel (from the shared-memory budget)
+  int32_t iterations[kGenMaxDense] = {};  // DenseLayer._iteration per dense layer: actor layers, then critic layers
+  float* d_params = nullptr;    // [n_total] actor | critic
+  float* d_grads = nullptr;     // [grad_floats]
   float* d_m = nullptr;         // Adam first moment
   float* d_v = nullptr;         // Adam second moment
-  float* d_partials = nullptr;  // [sm_count][kGradFloats]
+  float* d_partials = nullptr;  // [2 * sm_count][grad_floats]
   // staging for the host-pointer entry points (grown on demand)
   float* d_stage = nullptr;
   size_t stage_floats = 0;
@@ -63,11 +68,48 @@ static bool is_default_topology(int32_t state_size, int32_t action_size, const i
   return true;
 }
 
+static bool use_generic(const wb_policy* p) { return !p->default_topology || p->variant == 2; }
+
 static cudaError_t run_mlp(wb_policy* p, const MlpParams& m) {
+  if (use_generic(p)) {
+    GenParams g{};
+    g.actor = p->actor;
+    g.critic = p->critic;
+    g.params = m.params;
+    g.n = m.n;
+    g.mode = m.mode;
+    g.ts = p->gen_ts;
+    g.grad_floats = p->grad_floats;
+    g.states = m.states;
+    g.actions = m.actions;
+    g.old_logp = m.old_logp;
+    g.advantages = m.advantages;
+    g.returns = m.returns;
+    g.uniforms = m.uniforms;
+    g.seed = m.seed;
+    g.step = m.step;
+    g.mean = m.mean;
+    g.value = m.value;
+    g.out_actions = m.out_actions;
+    g.out_logp = m.out_logp;
+    g.partials = m.partials;
+    g.log_std = m.log_std;
+    g.epsilon = m.epsilon;
+    g.batch_size = m.batch_size;
+    return launch_mlp_generic(g, generic_grid_for(m.n, p->gen_ts, p->sm_count), p->stream);
+  }
   if (p->variant == 1) return launch_mlp(m, mlp_grid_for(m.n, p->sm_count), p->stream);
   return launch_mlp_tc(m, tc_grid_for(m.n, p->sm_count), p->stream);
 }
-static int grid_of(const wb_policy* p, int n) { return p->variant == 1 ? mlp_grid_for(n, p->sm_count) : tc_grid_for(n, p->sm_count); }
+static int grid_of(const wb_policy* p, int n) {
+  if (use_generic(p)) return generic_grid_for(n, p->gen_ts, p->sm_count);
+  return p->variant == 1 ? mlp_grid_for(n, p->sm_count) : tc_grid_for(n, p->sm_count);
+}
+// per-CTA partials -> the gradient buffer (fixed order); also NeuralNetwork.Zero(): the buffer is overwritten
+static cudaError_t reduce_grads(wb_policy* p, int grid) {
+  if (use_generic(p)) return launch_reduce_partials_n(p->d_partials, grid, p->d_grads, p->grad_floats, p->stream);
+  return launch_reduce_partials(p->d_partials, grid, p->d_grads, p->stream);
+}
 
 static void fill_mlp_common(const wb_policy* p, MlpParams& m, int n, int mode) {
   m = MlpParams{};
@@ -77,6 +119,43 @@ static void fill_mlp_common(const wb_policy* p, MlpParams& m, int n, int mode) {
   m.log_std = p->hp.log_std;
   m.epsilon = p->hp.epsilon;
   m.batch_size = (float)p->hp.batch_size;
+}
+
+// PPOAgent.ParseLayers output (kinds / sizes) -> layer table; false when the DSL instance is outside what the kernels cover
+static bool build_net(int32_t input, const int32_t* kinds, const int32_t* sizes, int32_t n_layers, GenNet* net, const char** why) {
+  *net = GenNet{};
+  if (n_layers < 1 || n_layers > kGenMaxLayers) { *why = "a network holds 1..16 layers"; return false; }
+  if (input < 1 || input > kGenMaxWidth) { *why = "the state size must be 1..128"; return false; }
+  net->n_layers = n_layers;
+  net->input = input;
+  int width = input, cache = 0, off = 0;
+  for (int l = 0; l < n_layers; l++) {
+    GenLayer& L = net->L[l];
+    L.kind = kinds[l];
+    L.in = width;
+    L.cache_off = cache;
+    cache += width;
+    if (kinds[l] == WB_DENSE) {
+      if (sizes[l] < 1 || sizes[l] > kGenMaxWidth) { *why = "dense layer widths must be 1..128"; return false; }
+      L.out = sizes[l];
+      L.w_off = off;
+      off += L.out * L.in;
+      L.b_off = off;
+      off += L.out;
+      width = L.out;
+      net->n_dense++;
+    } else if (kinds[l] == WB_RELU || kinds[l] == WB_LEAKYRELU || kinds[l] == WB_TANH) {
+      L.out = width;
+    } else {
+      *why = "unknown layer kind";
+      return false;
+    }
+  }
+  if (net->n_dense < 1) { *why = "a network needs at least one dense layer"; return false; }
+  net->output = width;
+  net->n_params = off;
+  net->cache_floats = cache;
+  return true;
 }
 
 // a timed-out exchange leaves the ranks' weights out of step: refuse every later data-parallel update of this handle
@@ -95,33 +174,47 @@ int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t*
   WB_REQUIRE(out, "out is null");
   *out = nullptr;
   WB_REQUIRE(actor_kinds && actor_sizes && critic_kinds && critic_sizes, "null layer list");
-  if (!is_default_topology(state_size, action_size, actor_kinds, actor_sizes, actor_layers, critic_kinds, critic_sizes, critic_layers))
-    return fail(WB_ERR_UNSUPPORTED,
-                "the sm_100a kernels are specialised for the reference's default networks "
-                "\"Input |64| (LeakyReLU) |64| (LeakyReLU) |4| (TanH) Output\" / \"Input |64| (LeakyReLU) |1| Output\" "
-                "with 12 inputs (Hyperparameters.cs:91-92)");
+  GenNet actor, critic;
+  const char* why = "";
+  if (!build_net(state_size, actor_kinds, actor_sizes, actor_layers, &actor, &why)) return fail(WB_ERR_UNSUPPORTED, "actor network: %s", why);
+  if (!build_net(state_size, critic_kinds, critic_sizes, critic_layers, &critic, &why)) return fail(WB_ERR_UNSUPPORTED, "critic network: %s", why);
+  // PPOAgent.CreateNetworks checks the two output sizes (PPOAgent.cs:78-92); the host shim falls back to the defaults like the reference
+  if (actor.output != action_size) return fail(WB_ERR_INVALID, "the actor's last dense layer must have action_size outputs (PPOAgent.cs:86)");
+  if (critic.output != 1) return fail(WB_ERR_INVALID, "the critic's last dense layer must have one output (PPOAgent.cs:78)");
+  if (action_size > 64) return fail(WB_ERR_UNSUPPORTED, "action_size must be 1..64");
+  if (actor.n_dense + critic.n_dense > kGenMaxDense) return fail(WB_ERR_UNSUPPORTED, "at most 32 dense layers in both networks together");
+  const int gen_ts = generic_tile_samples(actor, critic);
+  if (gen_ts == 0) return fail(WB_ERR_UNSUPPORTED, "the layer caches of one sample exceed shared memory (sum of layer widths too large)");
   if (int32_t rc = require_device()) return rc;
   wb_policy* p = new (std::nothrow) wb_policy();
   WB_REQUIRE(p, "out of host memory");
+  p->default_topology = is_default_topology(state_size, action_size, actor_kinds, actor_sizes, actor_layers, critic_kinds, critic_sizes, critic_layers);
+  p->actor = actor;
+  p->critic = critic;
+  p->n_actor = actor.n_params;
+  p->n_critic = critic.n_params;
+  p->n_total = actor.n_params + critic.n_params;
+  p->grad_floats = (p->n_total + 3 + 3) / 4 * 4;
+  p->gen_ts = gen_ts;
   cudaGetDevice(&p->device);
   cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
   if (hp) p->hp = *hp; else wb_hyperparams_default(&p->hp);
   // (any failure below releases what was allocated so far: nothing leaks behind a failed create)
-  cudaError_t e = cudaMalloc(&p->d_params, sizeof(float) * kTotalParams);
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_grads, sizeof(float) * kGradFloats);
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_m, sizeof(float) * kTotalParams);
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_v, sizeof(float) * kTotalParams);
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_partials, sizeof(float) * kGradFloats * (size_t)p->sm_count);
+  cudaError_t e = cudaMalloc(&p->d_params, sizeof(float) * p->n_total);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_grads, sizeof(float) * p->grad_floats);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_m, sizeof(float) * p->n_total);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_v, sizeof(float) * p->n_total);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_partials, sizeof(float) * p->grad_floats * (size_t)(2 * p->sm_count));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_norm_stats, sizeof(double) * 2 * kNormCtas);
   if (e == cudaSuccess) e = cudaHostAlloc(&p->h_comm_status, sizeof(uint32_t), cudaHostAllocMapped);
   if (e == cudaSuccess) {
     *p->h_comm_status = 0;
     e = cudaHostGetDevicePointer(&p->d_comm_status, p->h_comm_status, 0);
   }
-  if (e == cudaSuccess) e = cudaMemset(p->d_params, 0, sizeof(float) * kTotalParams);
-  if (e == cudaSuccess) e = cudaMemset(p->d_grads, 0, sizeof(float) * kGradFloats);
-  if (e == cudaSuccess) e = cudaMemset(p->d_m, 0, sizeof(float) * kTotalParams);
-  if (e == cudaSuccess) e = cudaMemset(p->d_v, 0, sizeof(float) * kTotalParams);
+  if (e == cudaSuccess) e = cudaMemset(p->d_params, 0, sizeof(float) * p->n_total);
+  if (e == cudaSuccess) e = cudaMemset(p->d_grads, 0, sizeof(float) * p->grad_floats);
+  if (e == cudaSuccess) e = cudaMemset(p->d_m, 0, sizeof(float) * p->n_total);
+  if (e == cudaSuccess) e = cudaMemset(p->d_v, 0, sizeof(float) * p->n_total);
   if (e != cudaSuccess) {
     wb_policy_destroy(p);
     return fail(WB_ERR_CUDA, "wb_policy_create: %s", cudaGetErrorString(e));
@@ -155,7 +248,9 @@ int32_t wb_policy_set_stream(wb_policy* p, void* cuda_stream) {
 
 int32_t wb_policy_set_variant(wb_policy* p, int32_t variant) {
   WB_REQUIRE(p, "policy is null");
-  WB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (tensor-core) or 1 (CUDA-core)");
+  WB_REQUIRE(variant == 0 || variant == 1 || variant == 2, "variant must be 0 (tensor-core), 1 (CUDA-core) or 2 (any-topology kernel)");
+  if (!p->default_topology && variant != 2)
+    return fail(WB_ERR_UNSUPPORTED, "variants 0 and 1 are specialised for the reference's default networks; this policy runs the any-topology kernel");
   p->variant = variant;
   return WB_OK;
 }
@@ -172,13 +267,13 @@ int32_t wb_policy_set_hyperparams(wb_policy* p, const wb_hyperparams* hp) {
   return WB_OK;
 }
 
-static int32_t which_range(int32_t which, int* off, int* count) {
+static int32_t which_range(const wb_policy* p, int32_t which, int* off, int* count) {
   if (which == 0) {
     *off = 0;
-    *count = kActorParams;
+    *count = p->n_actor;
   } else if (which == 1) {
-    *off = kActorParams;
-    *count = kCriticParams;
+    *off = p->n_actor;
+    *count = p->n_critic;
   } else {
     return fail(WB_ERR_INVALID, "which must be 0 (actor) or 1 (critic)");
   }
@@ -188,14 +283,14 @@ static int32_t which_range(int32_t which, int* off, int* count) {
 int32_t wb_policy_num_params(const wb_policy* p, int32_t which, int32_t* n_out) {
   WB_REQUIRE(p && n_out, "null argument");
   int off, count;
-  if (int32_t rc = which_range(which, &off, &count)) return rc;
+  if (int32_t rc = which_range(p, which, &off, &count)) return rc;
   *n_out = count;
   return WB_OK;
 }
 
 static int32_t copy_range(wb_policy* p, float* dev_base, int32_t which, const float* src_host, float* dst_host) {
   int off, count;
-  if (int32_t rc = which_range(which, &off, &count)) return rc;
+  if (int32_t rc = which_range(p, which, &off, &count)) return rc;
   if (src_host) WB_CUDA(cudaMemcpyAsync(dev_base + off, src_host, sizeof(float) * count, cudaMemcpyHostToDevice, p->stream));
   if (dst_host) WB_CUDA(cudaMemcpyAsync(dst_host, dev_base + off, sizeof(float) * count, cudaMemcpyDeviceToHost, p->stream));
   WB_CUDA(cudaStreamSynchronize(p->stream));
@@ -219,7 +314,7 @@ int32_t wb_policy_get_adam(wb_policy* p, int32_t which, float* m_host, float* v_
   WB_REQUIRE(p && m_host && v_host && iterations_host, "null argument");
   if (int32_t rc = copy_range(p, p->d_m, which, nullptr, m_host)) return rc;
   if (int32_t rc = copy_range(p, p->d_v, which, nullptr, v_host)) return rc;
-  const int first = which == 0 ? 0 : 3, cnt = which == 0 ? 3 : 2;
+  const int first = which == 0 ? 0 : p->actor.n_dense, cnt = which == 0 ? p->actor.n_dense : p->critic.n_dense;
   for (int i = 0; i < cnt; i++) iterations_host[i] = p->iterations[first + i];
   return WB_OK;
 }
@@ -228,7 +323,7 @@ int32_t wb_policy_set_adam(wb_policy* p, int32_t which, const float* m_host, con
   WB_REQUIRE(p && m_host && v_host && iterations_host, "null argument");
   if (int32_t rc = copy_range(p, p->d_m, which, m_host, nullptr)) return rc;
   if (int32_t rc = copy_range(p, p->d_v, which, v_host, nullptr)) return rc;
-  const int first = which == 0 ? 0 : 3, cnt = which == 0 ? 3 : 2;
+  const int first = which == 0 ? 0 : p->actor.n_dense, cnt = which == 0 ? p->actor.n_dense : p->critic.n_dense;
   for (int i = 0; i < cnt; i++) p->iterations[first + i] = iterations_host[i];
   return WB_OK;
 }
@@ -250,14 +345,15 @@ int32_t wb_policy_forward_dev(wb_policy* p, int32_t n, const float* states_dev, 
 int32_t wb_policy_forward(wb_policy* p, int32_t n, const float* states_host, float* mean_host, float* value_host) {
   WB_REQUIRE(p && states_host, "null argument");
   WB_REQUIRE(n > 0, "n must be positive");
+  const size_t IN = (size_t)p->actor.input, ACT = (size_t)p->actor.output;
   const size_t N = (size_t)n;
-  if (int32_t rc = ensure_stage(p, N * (kIn + kAct + 1))) return rc;
+  if (int32_t rc = ensure_stage(p, N * (IN + ACT + 1))) return rc;
   float* d_states = p->d_stage;
-  float* d_mean = d_states + N * kIn;
-  float* d_value = d_mean + N * kAct;
-  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * kIn, cudaMemcpyHostToDevice, p->stream));
+  float* d_mean = d_states + N * IN;
+  float* d_value = d_mean + N * ACT;
+  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * IN, cudaMemcpyHostToDevice, p->stream));
   if (int32_t rc = wb_policy_forward_dev(p, n, d_states, d_mean, d_value)) return rc;
-  if (mean_host) WB_CUDA(cudaMemcpyAsync(mean_host, d_mean, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
+  if (mean_host) WB_CUDA(cudaMemcpyAsync(mean_host, d_mean, sizeof(float) * N * ACT, cudaMemcpyDeviceToHost, p->stream));
   if (value_host) WB_CUDA(cudaMemcpyAsync(value_host, d_value, sizeof(float) * N, cudaMemcpyDeviceToHost, p->stream));
   WB_CUDA(cudaStreamSynchronize(p->stream));
   return WB_OK;
@@ -350,6 +446,7 @@ int32_t wb_gather_minibatch_dev(wb_policy* p, int32_t batch, const int32_t* inde
   WB_REQUIRE(p && index_dev && states_pool && actions_pool && logp_pool && advantages_pool && returns_pool, "null argument");
   WB_REQUIRE(states_out && actions_out && logp_out && advantages_out && returns_out, "null argument");
   WB_REQUIRE(batch > 0, "batch must be positive");
+  if (p->actor.input != kIn || p->actor.output != kAct) return fail(WB_ERR_UNSUPPORTED, "the minibatch gather is laid out for 12 observations and 4 actions");
   WB_CUDA(launch_gather_minibatch(index_dev, batch, states_pool, actions_pool, logp_pool, advantages_pool, returns_pool, states_out,
                                   actions_out, logp_out, advantages_out, returns_out, p->stream));
   p->launches++;
@@ -360,19 +457,20 @@ int32_t wb_policy_sample(wb_policy* p, int32_t n, const float* states_host, cons
                          float* logp_host, float* mean_host) {
   WB_REQUIRE(p && states_host && uniforms_host && actions_host && logp_host, "null argument");
   WB_REQUIRE(n > 0, "n must be positive");
+  const size_t IN = (size_t)p->actor.input, ACT = (size_t)p->actor.output;
   const size_t N = (size_t)n;
-  if (int32_t rc = ensure_stage(p, N * (kIn + kAct * 2 + kAct * 3))) return rc;
+  if (int32_t rc = ensure_stage(p, N * (IN + ACT * 2 + ACT * 3))) return rc;
   float* d_states = p->d_stage;
-  float* d_uni = d_states + N * kIn;
-  float* d_act = d_uni + N * kAct * 2;
-  float* d_logp = d_act + N * kAct;
-  float* d_mean = d_logp + N * kAct;
-  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * kIn, cudaMemcpyHostToDevice, p->stream));
-  WB_CUDA(cudaMemcpyAsync(d_uni, uniforms_host, sizeof(float) * N * kAct * 2, cudaMemcpyHostToDevice, p->stream));
+  float* d_uni = d_states + N * IN;
+  float* d_act = d_uni + N * ACT * 2;
+  float* d_logp = d_act + N * ACT;
+  float* d_mean = d_logp + N * ACT;
+  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * IN, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_uni, uniforms_host, sizeof(float) * N * ACT * 2, cudaMemcpyHostToDevice, p->stream));
   if (int32_t rc = wb_policy_sample_dev(p, n, d_states, d_uni, d_act, d_logp, d_mean)) return rc;
-  WB_CUDA(cudaMemcpyAsync(actions_host, d_act, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
-  WB_CUDA(cudaMemcpyAsync(logp_host, d_logp, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
-  if (mean_host) WB_CUDA(cudaMemcpyAsync(mean_host, d_mean, sizeof(float) * N * kAct, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaMemcpyAsync(actions_host, d_act, sizeof(float) * N * ACT, cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaMemcpyAsync(logp_host, d_logp, sizeof(float) * N * ACT, cudaMemcpyDeviceToHost, p->stream));
+  if (mean_host) WB_CUDA(cudaMemcpyAsync(mean_host, d_mean, sizeof(float) * N * ACT, cudaMemcpyDeviceToHost, p->stream));
   WB_CUDA(cudaStreamSynchronize(p->stream));
   return WB_OK;
 }
@@ -393,7 +491,7 @@ int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const 
   m.partials = p->d_partials;
   const int grid = grid_of(p, n);
   WB_CUDA(run_mlp(p, m));
-  WB_CUDA(launch_reduce_partials(p->d_partials, grid, p->d_grads, p->stream));
+  WB_CUDA(reduce_grads(p, grid));
   p->launches += 2;
   return WB_OK;
 }
@@ -401,6 +499,9 @@ int32_t wb_ppo_grad_dev(wb_policy* p, int32_t n, const float* states_dev, const 
 /* ---- fused gradient reduction + all-reduce over NVLink peer memory ---- */
 int32_t wb_comm_local_handle(wb_policy* p, void* handle64_out) {
   WB_REQUIRE(p && handle64_out, "null argument");
+  if (use_generic(p))
+    return fail(WB_ERR_UNSUPPORTED, "the fused NVLink gradient exchange is built for the default networks' 6152-float buffer; other topologies "
+                                    "all-reduce wb_policy_grad_buffer with NCCL (wb_ppo_grad_dev + all-reduce + wb_adam_step)");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   if (!p->d_exch) {
     WB_CUDA(cudaMalloc(&p->d_exch, kExchBytes));
@@ -449,6 +550,7 @@ int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_d
   WB_REQUIRE(n > 0, "n must be positive");
   WB_REQUIRE(p->hp.batch_size > 0, "batch_size must be positive");
   WB_REQUIRE(p->comm_world >= 1, "not connected: call wb_comm_local_handle / wb_comm_connect on every rank first");
+  WB_REQUIRE(!use_generic(p), "the fused exchange needs the default networks and kernel variant 0 or 1");
   if (int32_t rc = comm_healthy(p)) return rc;
   MlpParams m;
   fill_mlp_common(p, m, n, kModeGrad);
@@ -467,7 +569,17 @@ int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_d
   return WB_OK;
 }
 
-static void next_adam_params(wb_policy* p, AdamParams& a) {
+// DenseLayer.Adam bookkeeping: every dense layer's step counter advances (DenseLayer.cs:127) and its bias corrections are
+// (float)(1 - Math.Pow(beta, t)) (:142-145)
+static void next_corrections(wb_policy* p, float* corr1, float* corr2) {
+  const int n_dense = p->actor.n_dense + p->critic.n_dense;
+  for (int l = 0; l < n_dense; l++) {
+    p->iterations[l] += 1;
+    corr1[l] = (float)(1.0 - pow((double)p->hp.beta1, (double)p->iterations[l]));
+    corr2[l] = (float)(1.0 - pow((double)p->hp.beta2, (double)p->iterations[l]));
+  }
+}
+static void next_adam_params(wb_policy* p, AdamParams& a) {  // default networks: 3 + 2 dense layers
   a = AdamParams{};
   a.params = p->d_params;
   a.grads = p->d_grads;
@@ -477,11 +589,32 @@ static void next_adam_params(wb_policy* p, AdamParams& a) {
   a.beta1 = p->hp.beta1;
   a.beta2 = p->hp.beta2;
   a.eps = p->hp.adam_epsilon;
-  for (int l = 0; l < 5; l++) {
-    p->iterations[l] += 1;  // DenseLayer.cs:127
-    a.corr1[l] = (float)(1.0 - pow((double)p->hp.beta1, (double)p->iterations[l]));  // :142-145
-    a.corr2[l] = (float)(1.0 - pow((double)p->hp.beta2, (double)p->iterations[l]));
+  next_corrections(p, a.corr1, a.corr2);
+}
+static cudaError_t adam_any(wb_policy* p) {
+  if (p->default_topology) {
+    AdamParams a;
+    next_adam_params(p, a);
+    return launch_adam(a, p->stream);
   }
+  GenAdamParams g{};
+  g.params = p->d_params;
+  g.grads = p->d_grads;
+  g.m = p->d_m;
+  g.v = p->d_v;
+  g.n_params = p->n_total;
+  g.n_dense = p->actor.n_dense + p->critic.n_dense;
+  int k = 0;
+  for (int l = 0; l < p->actor.n_layers; l++)
+    if (p->actor.L[l].kind == WB_DENSE) g.layer_end[k++] = p->actor.L[l].b_off + p->actor.L[l].out;
+  for (int l = 0; l < p->critic.n_layers; l++)
+    if (p->critic.L[l].kind == WB_DENSE) g.layer_end[k++] = p->n_actor + p->critic.L[l].b_off + p->critic.L[l].out;
+  g.alpha = p->hp.alpha;
+  g.beta1 = p->hp.beta1;
+  g.beta2 = p->hp.beta2;
+  g.eps = p->hp.adam_epsilon;
+  next_corrections(p, g.corr1, g.corr2);
+  return launch_adam_generic(g, p->stream);
 }
 
 int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
@@ -500,6 +633,13 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
   m.partials = p->d_partials;
   const int grid = grid_of(p, n);
   WB_CUDA(run_mlp(p, m));
+  if (use_generic(p)) {  // any topology: reduction and Adam as separate launches (single rank; data-parallel callers use the NCCL path)
+    WB_REQUIRE(p->comm_world < 2, "a connected policy needs the default networks and kernel variant 0 or 1");
+    WB_CUDA(reduce_grads(p, grid));
+    WB_CUDA(adam_any(p));
+    p->launches += 3;
+    return WB_OK;
+  }
   AdamParams a;
   next_adam_params(p, a);
   const int world = p->comm_world >= 2 ? p->comm_world : 1;
@@ -514,21 +654,22 @@ int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const flo
                     const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host) {
   WB_REQUIRE(p && states_host && actions_host && old_logp_host && advantages_host && returns_host, "null argument");
   WB_REQUIRE(n > 0, "n must be positive");
+  const size_t IN = (size_t)p->actor.input, ACT = (size_t)p->actor.output;
   const size_t N = (size_t)n;
-  if (int32_t rc = ensure_stage(p, N * (kIn + kAct + kAct + 2))) return rc;
+  if (int32_t rc = ensure_stage(p, N * (IN + ACT + ACT + 2))) return rc;
   float* d_states = p->d_stage;
-  float* d_actions = d_states + N * kIn;
-  float* d_logp = d_actions + N * kAct;
-  float* d_adv = d_logp + N * kAct;
+  float* d_actions = d_states + N * IN;
+  float* d_logp = d_actions + N * ACT;
+  float* d_adv = d_logp + N * ACT;
   float* d_ret = d_adv + N;
-  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * kIn, cudaMemcpyHostToDevice, p->stream));
-  WB_CUDA(cudaMemcpyAsync(d_actions, actions_host, sizeof(float) * N * kAct, cudaMemcpyHostToDevice, p->stream));
-  WB_CUDA(cudaMemcpyAsync(d_logp, old_logp_host, sizeof(float) * N * kAct, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(float) * N * IN, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_actions, actions_host, sizeof(float) * N * ACT, cudaMemcpyHostToDevice, p->stream));
+  WB_CUDA(cudaMemcpyAsync(d_logp, old_logp_host, sizeof(float) * N * ACT, cudaMemcpyHostToDevice, p->stream));
   WB_CUDA(cudaMemcpyAsync(d_adv, advantages_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
   WB_CUDA(cudaMemcpyAsync(d_ret, returns_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
   if (int32_t rc = wb_ppo_grad_dev(p, n, d_states, d_actions, d_logp, d_adv, d_ret)) return rc;
   float tail[3] = {0.f, 0.f, 0.f};
-  WB_CUDA(cudaMemcpyAsync(tail, p->d_grads + kGradLossV, sizeof(tail), cudaMemcpyDeviceToHost, p->stream));
+  WB_CUDA(cudaMemcpyAsync(tail, p->d_grads + p->n_total, sizeof(tail), cudaMemcpyDeviceToHost, p->stream));
   WB_CUDA(cudaStreamSynchronize(p->stream));
   if (losses_host) {
     losses_host[0] = tail[0];
@@ -540,9 +681,7 @@ int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const flo
 
 int32_t wb_adam_step(wb_policy* p) {
   WB_REQUIRE(p, "policy is null");
-  AdamParams a;
-  next_adam_params(p, a);
-  WB_CUDA(launch_adam(a, p->stream));
+  WB_CUDA(adam_any(p));
   p->launches++;
   return WB_OK;
 }
@@ -550,7 +689,7 @@ int32_t wb_adam_step(wb_policy* p) {
 int32_t wb_policy_grad_buffer(wb_policy* p, void** dev_ptr_out, int32_t* n_floats_out) {
   WB_REQUIRE(p && dev_ptr_out && n_floats_out, "null argument");
   *dev_ptr_out = p->d_grads;
-  *n_floats_out = kGradFloats;
+  *n_floats_out = p->grad_floats;
   return WB_OK;
 }
 

@@ -104,6 +104,55 @@ cudaError_t launch_gather_minibatch(const int32_t* index, int B, const float* st
                                     const float* adv, const float* ret, float* o_states, float* o_actions, float* o_logp, float* o_adv,
                                     float* o_ret, cudaStream_t stream);
 
+// ---- any topology the reference's DSL can describe (mlp_generic.cu)
+constexpr int kGenMaxLayers = 16;   // layers (dense + activation) per network
+constexpr int kGenMaxWidth = 128;   // widest layer / state size
+constexpr int kGenMaxDense = 32;    // dense layers of both networks together (Adam bias corrections)
+constexpr int kGenThreads = 256;
+struct GenLayer {
+  int32_t kind, in, out;       // WB_DENSE: in -> out; activation: in == out
+  int32_t w_off, b_off;        // dense: offsets inside THIS network's flat parameter vector (W[out][in] row-major, then b[out])
+  int32_t cache_off;           // offset of this layer's INPUT inside a sample's cache row (NeuralNetwork._cache)
+};
+struct GenNet {
+  int32_t n_layers, input, output, n_params, n_dense, cache_floats;  // cache_floats: sum of the layers' input widths
+  GenLayer L[kGenMaxLayers];
+};
+struct GenParams {
+  GenNet actor, critic;
+  const float* params;  // actor | critic
+  int32_t n, mode, ts, grad_floats;
+  const float* states;
+  const float* actions;
+  const float* old_logp;
+  const float* advantages;
+  const float* returns;
+  const float* uniforms;
+  uint64_t seed, step;
+  float* mean;
+  float* value;
+  float* out_actions;
+  float* out_logp;
+  float* partials;      // [grid][grad_floats]
+  float log_std, epsilon, batch_size;
+};
+struct GenAdamParams {
+  float* params;
+  const float* grads;
+  float* m;
+  float* v;
+  int32_t n_params, n_dense;
+  int32_t layer_end[kGenMaxDense];  // one past the last parameter of every dense layer (actor layers, then critic layers)
+  float corr1[kGenMaxDense], corr2[kGenMaxDense];
+  float alpha, beta1, beta2, eps;
+};
+size_t generic_smem_bytes(const GenNet& actor, const GenNet& critic, int ts);
+int generic_tile_samples(const GenNet& actor, const GenNet& critic);  // 0: the caches do not fit shared memory even for one sample
+int generic_grid_for(int n, int ts, int sm_count);
+cudaError_t launch_mlp_generic(const GenParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_reduce_partials_n(const float* partials, int nparts, float* grads, int n_floats, cudaStream_t stream);
+cudaError_t launch_adam_generic(const GenAdamParams& a, cudaStream_t stream);
+
 int tc_grid_for(int n, int sm_count);
 cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M, int N, int K, int a_mn, int b_mn, int passes,

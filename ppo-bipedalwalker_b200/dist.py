@@ -66,7 +66,8 @@ def connect_peers(agent) -> bool:
         return False
     rank, world = dist.get_rank(), dist.get_world_size()
     buf = (C.c_ubyte * 64)()
-    check(lib().wb_comm_local_handle(agent._h, buf))
+    if lib().wb_comm_local_handle(agent._h, buf) != 0:
+        return False  # not the default networks: the fused exchange does not apply, the NCCL all-reduce does
     cuda = dist.get_backend() == "nccl"
     mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda" if cuda else "cpu")
     gathered = [torch.empty_like(mine) for _ in range(world)]

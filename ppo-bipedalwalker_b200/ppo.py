@@ -4,7 +4,9 @@ Reference classes mirrored (method names and argument meaning kept; numpy arrays
   PPOAgent       Walker/PPO/PPOAgent.cs:23 ctor, :381 SampleActions, :147 Train(Trajectory), :218 Train(Batch), :192 Save
   NeuralNetwork  Walker/PPO/Network/NeuralNetwork.cs:52 FeedForward, :85 Optimise, :94 Load, :159 Save (via PPOAgent.actor/critic)
   Trajectory     Walker/PPO/Trajectory.cs
-The compute (forward, clipped-surrogate gradient, backward, Adam, returns) runs in the CUDA library; this file only
+The compute (forward, clipped-surrogate gradient, backward, Adam, returns) runs in the CUDA library -- for the reference's
+default networks on the tensor-core kernel, for any other network the DSL describes (PPOAgent.cs:96-143: dense widths 1..128,
+ReLU / LeakyReLU / TanH, any state / action size) on the any-topology kernel; this file only
 parses the network DSL, initialises weights (Xavier, host side like Matrix.FromXavier), shuffles mini-batches and
 reads/writes the reference's .weights text format.
 """
@@ -187,6 +189,11 @@ class PPOAgent:
         try:
             a_layers = ParseLayers(actor)
         except ValueError:
+            actor, a_layers = DEFAULT_ACTOR, ParseLayers(DEFAULT_ACTOR)
+        # the last dense layers must produce one value / actionSize means, else the defaults (PPOAgent.cs:78-92)
+        if [s for k, s in c_layers if k == DENSE][-1:] != [1]:
+            critic, c_layers = DEFAULT_CRITIC, ParseLayers(DEFAULT_CRITIC)
+        if [s for k, s in a_layers if k == DENSE][-1:] != [actionSize]:
             actor, a_layers = DEFAULT_ACTOR, ParseLayers(DEFAULT_ACTOR)
         ak = np.array([k for k, _ in a_layers], np.int32)
         asz = np.array([s for _, s in a_layers], np.int32)

@@ -255,9 +255,109 @@ def test_weights_file_roundtrip(gpu, O):
     assert not fourth.actor.Load(actor_lines + [actor_lines[1]])  # more lines than layers (the reference throws)
 
 
-def test_unsupported_topology_fails_loudly(gpu):
-    with pytest.raises(gpu.WalkerB200Error):
-        gpu.PPOAgent(actor="Input |32| (ReLU) |4| (TanH) Output")
+# user-edited Hyperparameters.ActorNeuralNetwork / CriticNeuralNetwork strings (PPOAgent.cs:96-143): (state, action, actor, critic)
+TOPOLOGIES = [
+    (12, 4, "Input |32| (ReLU) |4| (TanH) Output", "Input |16| (ReLU) |16| (TanH) |1| Output"),
+    (12, 4, "Input |128| (LeakyReLU) |48| (ReLU) |80| (TanH) |4| Output", "Input |96| (ReLU) |1| Output"),
+    (7, 3, "Input |20| (TanH) |3| Output", "Input |5| (LeakyReLU) |9| (LeakyReLU) |1| (ReLU) Output"),
+    (12, 4, "Input |4| Output", "Input |1| Output"),
+]
+
+
+def make_topology_pair(gpu, O, topo, seed, batch_size):
+    sdim, adim, actor_dsl, critic_dsl = topo
+    hp = gpu.default_hyperparams()
+    hp.batch_size = batch_size
+    agent = gpu.PPOAgent(sdim, adim, hp=hp, actor=actor_dsl, critic=critic_dsl, seed=seed)
+    assert agent.actor.structure == actor_dsl and agent.critic.structure == critic_dsl  # parsed, not replaced by the defaults
+    actor = O.Net(sdim, gpu.ParseLayers(actor_dsl))
+    critic = O.Net(sdim, gpu.ParseLayers(critic_dsl))
+    actor.set_params(agent.actor.get_flat())
+    critic.set_params(agent.critic.get_flat())
+    ohp = O.hyper_defaults()
+    ohp.batch_size = batch_size
+    return agent, actor, critic, ohp
+
+
+def topology_batch(rng, actor, n, sdim, adim):
+    states = rng.normal(size=(n, sdim)).astype(np.float32)
+    mean = actor.forward(states)
+    std = np.exp(np.float32(-1.0))
+    actions = (mean + std * rng.normal(size=(n, adim))).astype(np.float32)
+    logp = (-np.log(std) - np.log(np.sqrt(2 * np.pi)) - 0.5 * ((actions - mean) / std) ** 2).astype(np.float32)
+    old_logp = (logp + 0.2 * rng.normal(size=(n, adim))).astype(np.float32)
+    ratio = np.exp(logp.astype(np.float64) - old_logp)
+    old_logp[(np.abs(ratio - 1.3) < 1e-3) | (np.abs(ratio - 0.7) < 1e-3)] += np.float32(0.01)
+    return states, actions, old_logp, rng.normal(size=n).astype(np.float32), (3 * rng.normal(size=n)).astype(np.float32)
+
+
+@pytest.mark.parametrize("topo", TOPOLOGIES)
+def test_any_dsl_topology_runs_on_the_gpu_and_matches_the_oracle(gpu, O, topo):
+    """Networks other than the defaults -- ReLU, mixed widths up to 128, other state / action sizes, activation-free and
+    activation-terminated stacks -- run on the any-topology kernel: forward, sampling, PPOAgent.Train(Batch) gradients per dense
+    layer, losses, and five Adam steps against the per-sample oracle (NeuralNetwork.cs:52-82, DenseLayer.cs:82-159,
+    ActivationLayer.cs:32-73, PPOAgent.cs:218-346)."""
+    sdim, adim = topo[0], topo[1]
+    n = 333
+    agent, actor, critic, ohp = make_topology_pair(gpu, O, topo, 21, n)
+    rng = np.random.default_rng(21)
+    s = rng.normal(size=(n, sdim)).astype(np.float32)
+    mean, value = agent.FeedForward(s)
+    np.testing.assert_allclose(mean, actor.forward(s), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(value, critic.forward(s)[:, 0], rtol=1e-5, atol=1e-6)
+    u = rng.random((n, adim, 2)).astype(np.float32)
+    a, lp, mu, std = agent.SampleActions(s, u)
+    for i in range(0, n, 37):
+        ra, rlp, rmu = O.sample_actions(actor, ohp, s[i], u[i].ravel())
+        np.testing.assert_allclose(a[i], ra, rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(lp[i], rlp, rtol=1e-4, atol=2e-5)
+    batch = topology_batch(rng, actor, n, sdim, adim)
+    closs, aloss, skipped = agent.Gradients(*batch)
+    rskip, rcl, ral = O.ppo_train_batch(actor, critic, ohp, *batch, optimise=False)
+    assert skipped == rskip == 0
+    for got, ref, net in ((agent.actor.get_grads(), actor.get_grads(), agent.actor), (agent.critic.get_grads(), critic.get_grads(), agent.critic)):
+        p = 0
+        for out, inp in net.shapes:  # every dense layer's dW and db against that layer's own largest entry
+            for cnt in (out * inp, out):
+                g, r = got[p:p + cnt], ref[p:p + cnt]
+                p += cnt
+                assert np.abs(g - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-12), (net.structure, out, inp)
+    assert abs(closs - rcl) <= 1e-4 * max(1.0, abs(rcl)) and abs(aloss - ral) <= 1e-4 * max(1.0, abs(ral))
+    for it in range(5):
+        b = topology_batch(rng, actor, n, sdim, adim)
+        agent.TrainBatch(*b)
+        O.ppo_train_batch(actor, critic, ohp, *b, optimise=True)
+        assert np.abs(agent.actor.get_flat() - actor.get_params()).max() < 2e-5, f"actor weights diverged at Adam step {it}"
+        assert np.abs(agent.critic.get_flat() - critic.get_params()).max() < 2e-5
+    m, v, iters = agent.actor.get_adam()
+    assert list(iters) == [5] * len(agent.actor.shapes)
+
+
+def test_the_three_policy_kernels_agree_on_the_default_networks(gpu, O):
+    """The any-topology kernel (variant 2) is a third implementation of the default networks: same gradients as the tensor-core
+    (0) and CUDA-core (1) kernels and as the oracle, on a batch with a skipped sample."""
+    n = 2000
+    grads = {}
+    for variant in (0, 1, 2):
+        agent, actor, critic, ohp = make_pair(gpu, O, 7, n, variant=variant)
+        rng = np.random.default_rng(7)
+        batch = list(synth_batch(rng, actor, n, critic_flat=critic.get_params()))
+        batch[2][11, 1] = -200.0  # old probability underflows -> sample skipped (PPOAgent.cs:286-290)
+        closs, aloss, skipped = agent.Gradients(*batch)
+        assert skipped == 1
+        grads[variant] = np.concatenate([agent.actor.get_grads(), agent.critic.get_grads()])
+    rskip, rcl, ral = O.ppo_train_batch(actor, critic, ohp, *batch, optimise=False)
+    ref = np.concatenate([actor.get_grads(), critic.get_grads()])
+    for variant in (0, 1, 2):
+        assert rel_err(grads[variant], ref) < 1e-4, variant
+
+
+def test_topologies_outside_the_kernels_fail_loudly(gpu):
+    with pytest.raises(gpu.WalkerB200Error):  # wider than the 128 the kernels cover: refused, never a silent fallback
+        gpu.PPOAgent(actor="Input |256| (ReLU) |4| (TanH) Output")
+    # a bad DSL string or a wrong output size falls back to the default network like PPOAgent.CreateNetworks (PPOAgent.cs:41-93)
+    agent = gpu.PPOAgent(actor="Input |32| (ReLU) |5| Output", critic="Input 64 Output")
+    assert agent.actor.structure == gpu.DEFAULT_ACTOR and agent.critic.structure == gpu.DEFAULT_CRITIC
 
 
 def test_train_one_episode_end_to_end(gpu, O):
