@@ -152,13 +152,18 @@ using namespace wb;
 
 // Lanes per environment when the caller does not choose: with few walkers per SM the step is latency bound and the lanes of
 // a walker split its SAT axes and vertices; with many, one lane per walker does no redundant work (see physics_lanes.cu).
+// The boundaries are read off profiles/variant_sweep_r2.log (scripts/variant_sweep.sh: every candidate variant timed from one
+// snapshot 512 env-steps into a random-action rollout, 1 ... 262 144 walkers on a 148-SM B200); each is where the faster variant
+// changes -- mostly where the narrower layout's warps stop fitting one wave (8 lanes: 12 warps per SM = 48 walkers; 4 lanes:
+// 19 warps per SM = 152 walkers).
 static int default_lanes(int n_envs, int sm_count) {
   const long per_sm = ((long)n_envs + sm_count - 1) / sm_count;
-  if (per_sm <= 10) return 32;  // a handful of walkers (the reference's single-walker case): all 32 lanes on one walker
-  if (per_sm <= 48) return 8;
-  if (per_sm <= 160) return 4;
-  if (per_sm <= 200) return 2;
-  return 1001;  // GPU full: one thread per walker with CTA-level work compaction
+  if (per_sm <= 10) return 32;   // a handful of walkers (the reference's single-walker case): all 32 lanes on one walker
+  if (per_sm <= 22) return 16;   // 2048 walkers: 0.315 ms (16) vs 0.325 (8) / 0.345 (32); 3072: 0.359 vs 0.366
+  if (per_sm <= 48) return 8;    // 4096: 0.375 (8) vs 0.416 (16) / 0.446 (4); 7104: 0.438 vs 0.510 (4)
+  if (per_sm <= 150) return 4;   // 8192: 0.508 (4) vs 0.688 (8); 16384: 0.725 vs 0.784 (2) / 0.945 (compacting)
+  if (per_sm <= 200) return 2;   // 23680: 0.900 (2) vs 1.075 (4); 28416: 0.937 vs 0.963 (compacting)
+  return 1001;  // GPU full: one thread per walker with CTA-level work compaction (32768: 0.968 vs 1.092 (2))
 }
 
 struct wb_env_batch {
