@@ -294,6 +294,22 @@ struct TcConsts {
   float stdv, neg_log_std, log_sqrt_2pi, upper, lower, variance;
 };
 
+// -DWB_TC_PROFILE (experiment builds only): cycles thread 0 of every CTA spends in each phase of a tile, summed over CTAs
+#ifdef WB_TC_PROFILE
+__device__ unsigned long long g_tc_prof[16];
+#define TC_MARK(k)                                                       \
+  do {                                                                   \
+    if (tid == 0) {                                                      \
+      long long now_;                                                    \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_)::"memory");    \
+      tc_acc[k] += (unsigned long long)(now_ - tc_t);                    \
+      tc_t = now_;                                                       \
+    }                                                                    \
+  } while (0)
+#else
+#define TC_MARK(k)
+#endif
+
 __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p, const TcConsts gc) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -401,6 +417,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     }
   };
   prefetch(blockIdx.x);
+#ifdef WB_TC_PROFILE
+  unsigned long long tc_acc[12] = {};
+  long long tc_t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc_t)::"memory");
+#endif
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int s0 = tile * kS;
     const int nvalid = min(kS, p.n - s0);
@@ -427,6 +448,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncthreads();
     tc::fence_after_thread_sync();
 
+    TC_MARK(0);  // P0: stage X + sync
     // ---- P1: F1 = [X|1] x [W1|b1 ; Wc1|bc1]^T  -> 128 columns
     if (issuer) {
       issue_range(S.mma, kChainF1, kChainF2, tmem, any_tile);
@@ -437,6 +459,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncwarp();
     tc::fence_after_thread_sync();
 
+    TC_MARK(1);  // P1: F1 MMA + wait
     // ---- P2: half 0: A1 = leaky(F1[:, 0:64]); half 1: C1 = leaky(F1[:, 64:128]), V = Wc2 . C1 + bc2 (left to right).
     //      The sign masks (LeakyReLU derivative) stay with the half that owns the columns.
     unsigned mask1[2] = {0u, 0u};  // half 0: A1 < 0 per column; half 1: C1 < 0 per column
@@ -472,6 +495,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncthreads();
     tc::fence_after_thread_sync();
 
+    TC_MARK(2);  // P2: A1 / C1 epilogue + sync
     // ---- P3: F2 = A1 x W2^T
     if (issuer) {
       issue_range(S.mma, kChainF2, kChainDW3, tmem, any_tile);
@@ -482,6 +506,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncwarp();
     tc::fence_after_thread_sync();
 
+    TC_MARK(3);  // P3: F2 MMA + wait
     // ---- P4: each half: A2 = leaky(F2 + b2) for its 32 columns and its partial W3 . A2; the partials meet in shared memory
     unsigned maskA2 = 0u;  // own 32 columns
     if (epi) {
@@ -545,6 +570,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       continue;
     }
 
+    TC_MARK(4);  // P4: A2 epilogue, mu
     // ---- per-sample clipped-surrogate gradient (PPOAgent.cs:232-326), tanh backward: computed by BOTH halves (each needs
     //      g3 for its columns of G2); half 0 keeps the actor-side sums, half 1 the critic side and stages [g3 | gv]
     float g3[kAct] = {0.f, 0.f, 0.f, 0.f}, gv = 0.f;
@@ -616,6 +642,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncthreads();
     tc::fence_after_thread_sync();
 
+    TC_MARK(5);  // surrogate gradient + g3v staging + sync
     // ---- P5: [C1|A2]^T x [g3|gv]  (accumulates dWc2 and dW3 over all tiles)
     if (issuer) {
       issue_range(S.mma, kChainDW3, kChainB2, tmem, any_tile);
@@ -625,6 +652,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     phase ^= 1;
     __syncwarp();
     tc::fence_after_thread_sync();
+    TC_MARK(6);  // P5: dW3 MMA + wait
     // dL/dz2 = (W3^T g3) * leaky'(z2) for the half's 32 columns (sum over k from 0, Matrix.Multiply order)
     if (epi) {
       const int c0 = half * 32;
@@ -649,9 +677,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncthreads();
     tc::fence_after_thread_sync();
 
+    TC_MARK(7);  // G2 epilogue + sync
     // ---- P6: dL/dA1 = G2 x W2 ; dW2 += G2^T x A1 ; dB2 += G2^T x [X|1]
     if (issuer) {
+#ifdef WB_TC_INTERLEAVE
+      // the three chains write different accumulators: issue them round-robin so that consecutive MMAs are independent
+#pragma unroll 4
+      for (int i = 0; i < 24; i++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const MmaEntry e = S.mma[kChainB2 + c * 24 + i];
+          tc::mma_tf32(tmem + e.tmem_col, e.da, e.db, e.idesc, e.acc_mode == 1u || (e.acc_mode == 2u && any_tile));
+        }
+      }
+#else
       issue_range(S.mma, kChainB2, kChainDW1, tmem, any_tile);
+#endif
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -659,6 +700,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncwarp();
     tc::fence_after_thread_sync();
 
+    TC_MARK(8);  // P6: B2 / dW2 / dB2 MMA + wait
     // ---- P7: half 0: G1 = dL/dA1 * leaky'(z1) -> overwrites A1; half 1: Gc1 = (Wc2^T gv) * leaky'(zc1) -> overwrites C1
     if (epi) {
       float* hi_t = S.act_hi + half * 2 * kBlk;
@@ -687,6 +729,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncthreads();
     tc::fence_after_thread_sync();
 
+    TC_MARK(9);  // P7: G1 / Gc1 epilogue + sync
     // ---- P8: [G1|Gc1]^T x [X|1]  (accumulates dW1, db1, dWc1, dbc1)
     if (issuer) {
       issue_range(S.mma, kChainDW1, kMmaEntries, tmem, any_tile);
@@ -697,7 +740,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     __syncwarp();
     tc::fence_after_thread_sync();
     any_tile = true;
+    TC_MARK(10);  // P8: dW1 MMA + wait
   }
+#ifdef WB_TC_PROFILE
+  if (tid == 0) {
+    for (int k = 0; k < 11; k++) atomicAdd(&g_tc_prof[k], tc_acc[k]);
+    atomicAdd(&g_tc_prof[11], 1ull);
+  }
+#endif
 
   if (grad) {
     // ---- per-CTA partial gradient straight out of TMEM (flat parameter layout of mlp.cuh), warps 0..3
@@ -767,6 +817,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
 }
+
+#ifdef WB_TC_PROFILE
+extern "C" int wb_tc_prof_read(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int tc_grid_for(int n, int sm_count) {
   const int ntiles = (n + kS - 1) / kS;
