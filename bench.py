@@ -180,14 +180,14 @@ def cpu_ppo_baseline(O, actor_flat, critic_flat, batch, budget_s=10.0):
     hp = O.hyper_defaults()
     hp.batch_size = PPO_SAMPLES
     done, t0, chunk = 0, time.perf_counter(), 8192
-    while done < PPO_SAMPLES and (done == 0 or time.perf_counter() - t0 < budget_s):
-        sl = slice(done, done + chunk)
+    while done == 0 or time.perf_counter() - t0 < budget_s:   # whole passes over the minibatch until the budget is used
+        sl = slice(done % PPO_SAMPLES, done % PPO_SAMPLES + chunk)
         O.ppo_train_batch(actor, critic, hp, *[x[sl] for x in batch], optimise=True)
         done += chunk
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "samples/s", "cores": 1, "kind": "port",
-            "sample": f"{done} of the {PPO_SAMPLES} samples in chunks of {chunk} (forward + clipped-surrogate gradient + backward per sample, "
-                      f"Adam per chunk), one thread, {dt:.1f} s"}
+            "sample": f"{done} samples = {done / PPO_SAMPLES:.1f} passes over the {PPO_SAMPLES}-sample minibatch in chunks of {chunk} (forward + "
+                      f"clipped-surrogate gradient + backward per sample, Adam per chunk), one thread, {dt:.1f} s"}
 
 
 def cfg1_cpu(O, env_steps=1500, train_samples=8192):
