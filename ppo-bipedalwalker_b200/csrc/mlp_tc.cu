@@ -168,17 +168,6 @@ constexpr int kBlk = kS * 32;    // floats in one 32-feature block of a 64-row t
 // Gc1 and columns 32..63 of A2/G2), so the per-sample element-wise work of a tile is spread over 128 threads; warp 8: MMA issuer
 constexpr int kTcThreads = 288;
 
-// ---- pre-built MMA programs.  All operand tiles live at fixed shared-memory addresses, so every tcgen05.mma of a tile's
-// pipeline (150 of them) has constant descriptors: they are built ONCE per CTA, in parallel, into a table, and the issuing
-// thread only streams entries (one LDS.128 pair + one tcgen05.mma each) instead of rebuilding 64-bit descriptors per k-step.
-struct __align__(16) MmaEntry {
-  uint64_t da, db;
-  uint32_t tmem_col, idesc;
-  uint32_t acc_mode;  // 0: overwrite (first MMA of a fresh accumulator), 1: accumulate, 2: accumulate unless first tile of the CTA
-  uint32_t pad;
-};
-constexpr int kChainF1 = 0, kChainF2 = 6, kChainDW3 = 30, kChainB2 = 54, kChainDW2 = 78, kChainDB2 = 102, kChainDW1 = 126, kMmaEntries = 150;
-
 struct __align__(1024) TcSmem {
   float xt_hi[kBlk], xt_lo[kBlk];            // [X(12) | 1 | 0 0 0] per sample
   float act_hi[6 * kBlk], act_lo[6 * kBlk];  // blocks 0-1: A1 -> G1, 2-3: C1 -> Gc1, 4-5: A2 -> G2
@@ -187,7 +176,6 @@ struct __align__(1024) TcSmem {
   float w1_hi[128 * 32], w1_lo[128 * 32];    // rows = [W1 o | Wc1 o] (128), features = [i(12) | bias | 0 0 0]
   float w3[kAct * kHid], wc2[kHid], b2[kHid], b3[kAct], bc2[4];
   float mu_part[2][kS][kAct];  // the two halves' partial W3 . A2 sums
-  MmaEntry mma[kMmaEntries];
   float red[512];
   uint64_t mbar;
   uint32_t tmem_slot;
@@ -199,61 +187,33 @@ constexpr uint32_t kTmemCols = 512;
 
 enum : int { kKMajor = 0, kMnMajor = 1 };
 
-// one 3xTF32 MMA chain: D[tmem] (+)= A * B over `ksteps` k-steps of 8
-//   K-major tile  (rows x features): k-step advances 32 B inside a 128-B row; every 4 k-steps the next 32-feature block (rows*128 B)
-//   MN-major tile (features x rows): k-step advances 8 rows = 1024 B; LBO = rows*128 B between 32-feature blocks
-__device__ __forceinline__ void issue_chain(uint32_t tmem_d, int M, int N, const float* a_hi, const float* a_lo, int a_major, int a_rows,
-                                            const float* b_hi, const float* b_lo, int b_major, int b_rows, int ksteps, bool accumulate) {
-  const uint32_t idesc = tc::make_idesc_tf32(M, N, a_major, b_major);
-  const uint32_t a_lbo = a_major == kMnMajor ? (uint32_t)a_rows * 128u : 0u;
-  const uint32_t b_lbo = b_major == kMnMajor ? (uint32_t)b_rows * 128u : 0u;
-  bool acc = accumulate;
-#pragma unroll 1
+// operand tile geometry of the B32 layout:
+//   K-major tile  (rows x features): a k-step advances 32 B inside a 128-B row; every 4 k-steps the next 32-feature block (rows*128 B)
+//   MN-major tile (features x rows): a k-step advances 8 rows = 1024 B; LBO = rows*128 B between 32-feature blocks
+// One 3xTF32 MMA chain with COMPILE-TIME operand geometry: the descriptors of all 3 * KSTEPS MMAs are the chain's base
+// descriptors (built once from the tiles' shared-memory addresses, which are the same in every thread) plus constants, so the
+// issuing thread's instruction stream is straight-line uniform-datapath arithmetic + UTCHMMA.  The table-driven issue it replaces
+// fetched every descriptor with LDS and moved six words through R2UR behind an elect / retry loop per MMA: ~95 cycles of
+// issue per MMA whatever its shape (profiles/phase_profile_ppo_tc_r2.log), i.e. the tensor pipe waited for its own issuer.
+template <int M, int N, int A_MAJOR, int A_ROWS, int B_MAJOR, int B_ROWS, int KSTEPS>
+__device__ __forceinline__ void issue_chain_ct(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, bool accumulate_first) {
+  constexpr uint32_t idesc = tc::make_idesc_tf32(M, N, A_MAJOR, B_MAJOR);
+  constexpr uint32_t a_lbo = A_MAJOR == kMnMajor ? (uint32_t)A_ROWS * 128u : 0u;
+  constexpr uint32_t b_lbo = B_MAJOR == kMnMajor ? (uint32_t)B_ROWS * 128u : 0u;
+  const uint64_t da_hi = tc::make_smem_desc(a_hi, a_lbo, 512u) | kLayoutB32, da_lo = tc::make_smem_desc(a_lo, a_lbo, 512u) | kLayoutB32;
+  const uint64_t db_hi = tc::make_smem_desc(b_hi, b_lbo, 512u) | kLayoutB32, db_lo = tc::make_smem_desc(b_lo, b_lbo, 512u) | kLayoutB32;
+#pragma unroll
   for (int pass = 0; pass < 3; pass++) {
-    const uint32_t a_base = tc::smem_u32(pass == 1 ? a_lo : a_hi);
-    const uint32_t b_base = tc::smem_u32(pass == 2 ? b_lo : b_hi);
-#pragma unroll 1
-    for (int ks = 0; ks < ksteps; ks++) {
-      const uint32_t a_off = a_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * a_rows * 128u + (uint32_t)(ks & 3) * 32u;
-      const uint32_t b_off = b_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * b_rows * 128u + (uint32_t)(ks & 3) * 32u;
-      const uint64_t da = tc::make_smem_desc(a_base + a_off, a_lbo, 512u) | kLayoutB32;
-      const uint64_t db = tc::make_smem_desc(b_base + b_off, b_lbo, 512u) | kLayoutB32;
-      tc::mma_tf32(tmem_d, da, db, idesc, acc);
-      acc = true;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ks++) {
+      // byte offset of k-step ks inside the tile (>> 4: the descriptor's start-address field counts 16-byte units; every tile
+      // lies below 256 KB, so the sum never carries out of the 14-bit field)
+      const uint32_t a_off = A_MAJOR == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * A_ROWS * 128u + (uint32_t)(ks & 3) * 32u;
+      const uint32_t b_off = B_MAJOR == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * B_ROWS * 128u + (uint32_t)(ks & 3) * 32u;
+      const uint64_t da = (pass == 1 ? da_lo : da_hi) + (uint64_t)(a_off >> 4);
+      const uint64_t db = (pass == 2 ? db_lo : db_hi) + (uint64_t)(b_off >> 4);
+      tc::mma_tf32(tmem_d, da, db, idesc, (pass == 0 && ks == 0) ? accumulate_first : true);
     }
-  }
-}
-
-// entries [first, first + 3 * ksteps) = one 3xTF32 chain (same operand addressing as issue_chain); `persistent`: the
-// accumulator lives across tiles (weight gradients)
-__device__ __forceinline__ void build_chain(MmaEntry* table, int first, uint32_t tmem_col, int M, int N, const float* a_hi, const float* a_lo,
-                                            int a_major, int a_rows, const float* b_hi, const float* b_lo, int b_major, int b_rows, int ksteps,
-                                            bool persistent) {
-  const uint32_t idesc = tc::make_idesc_tf32(M, N, a_major, b_major);
-  const uint32_t a_lbo = a_major == kMnMajor ? (uint32_t)a_rows * 128u : 0u;
-  const uint32_t b_lbo = b_major == kMnMajor ? (uint32_t)b_rows * 128u : 0u;
-  for (int i = threadIdx.x; i < 3 * ksteps; i += blockDim.x) {
-    const int pass = i / ksteps, ks = i % ksteps;
-    const uint32_t a_base = tc::smem_u32(pass == 1 ? a_lo : a_hi);
-    const uint32_t b_base = tc::smem_u32(pass == 2 ? b_lo : b_hi);
-    const uint32_t a_off = a_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * a_rows * 128u + (uint32_t)(ks & 3) * 32u;
-    const uint32_t b_off = b_major == kMnMajor ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * b_rows * 128u + (uint32_t)(ks & 3) * 32u;
-    MmaEntry e;
-    e.da = tc::make_smem_desc(a_base + a_off, a_lbo, 512u) | kLayoutB32;
-    e.db = tc::make_smem_desc(b_base + b_off, b_lbo, 512u) | kLayoutB32;
-    e.tmem_col = tmem_col;
-    e.idesc = idesc;
-    e.acc_mode = i > 0 ? 1u : (persistent ? 2u : 0u);
-    e.pad = 0u;
-    table[first + i] = e;
-  }
-}
-
-__device__ __forceinline__ void issue_range(const MmaEntry* table, int begin, int end, uint32_t tmem, bool any_tile) {
-#pragma unroll 4
-  for (int i = begin; i < end; i++) {
-    const MmaEntry e = table[i];
-    tc::mma_tf32(tmem + e.tmem_col, e.da, e.db, e.idesc, e.acc_mode == 1u || (e.acc_mode == 2u && any_tile));
   }
 }
 
@@ -367,19 +327,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   }
   if (tid < kAct) S.b3[tid] = p.params[kOffB3 + tid];
   if (tid == 0) S.bc2[0] = p.params[kOffBc2];
-  build_chain(S.mma, kChainF1, kColF1, 64, 128, S.xt_hi, S.xt_lo, kKMajor, kS, S.w1_hi, S.w1_lo, kKMajor, 128, 2, false);
-  build_chain(S.mma, kChainF2, kColF2, 64, 64, S.act_hi, S.act_lo, kKMajor, kS, S.w2_hi, S.w2_lo, kKMajor, kHid, 8, false);
-  build_chain(S.mma, kChainDW3, kColDW3, 128, 8, S.act_hi + 2 * kBlk, S.act_lo + 2 * kBlk, kMnMajor, kS, S.g3v_hi, S.g3v_lo, kMnMajor, kS, 8, true);
-  build_chain(S.mma, kChainB2, kColB2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kKMajor, kS, S.w2_hi, S.w2_lo, kMnMajor, kHid, 8, false);
-  build_chain(S.mma, kChainDW2, kColDW2, 64, 64, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.act_hi, S.act_lo, kMnMajor, kS, 8, true);
-  build_chain(S.mma, kChainDB2, kColDB2, 64, 16, S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, true);
-  build_chain(S.mma, kChainDW1, kColDW1, 128, 16, S.act_hi, S.act_lo, kMnMajor, kS, S.xt_hi, S.xt_lo, kMnMajor, kS, 8, true);
   tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = S.tmem_slot;
   const uint32_t tmem_warp = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  // shared-window byte addresses of the operand tiles (identical in every thread: the MMA descriptors derive from them by constants)
+  const uint32_t sm_xt_hi = tc::smem_u32(S.xt_hi), sm_xt_lo = tc::smem_u32(S.xt_lo);
+  const uint32_t sm_act_hi = tc::smem_u32(S.act_hi), sm_act_lo = tc::smem_u32(S.act_lo);
+  const uint32_t sm_g3v_hi = tc::smem_u32(S.g3v_hi), sm_g3v_lo = tc::smem_u32(S.g3v_lo);
+  const uint32_t sm_w2_hi = tc::smem_u32(S.w2_hi), sm_w2_lo = tc::smem_u32(S.w2_lo);
+  const uint32_t sm_w1_hi = tc::smem_u32(S.w1_hi), sm_w1_lo = tc::smem_u32(S.w1_lo);
+  constexpr uint32_t kBlkBytes = kBlk * 4;
   uint32_t phase = 0;
 
   float lossV = 0.f, lossA = 0.f, skipped = 0.f;
@@ -451,7 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(0);  // P0: stage X + sync
     // ---- P1: F1 = [X|1] x [W1|b1 ; Wc1|bc1]^T  -> 128 columns
     if (issuer) {
-      issue_range(S.mma, kChainF1, kChainF2, tmem, any_tile);
+      issue_chain_ct<64, 128, kKMajor, kS, kKMajor, 128, 2>(tmem + kColF1, sm_xt_hi, sm_xt_lo, sm_w1_hi, sm_w1_lo, false);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -498,7 +458,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(2);  // P2: A1 / C1 epilogue + sync
     // ---- P3: F2 = A1 x W2^T
     if (issuer) {
-      issue_range(S.mma, kChainF2, kChainDW3, tmem, any_tile);
+      issue_chain_ct<64, 64, kKMajor, kS, kKMajor, kHid, 8>(tmem + kColF2, sm_act_hi, sm_act_lo, sm_w2_hi, sm_w2_lo, false);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -645,7 +605,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(5);  // surrogate gradient + g3v staging + sync
     // ---- P5: [C1|A2]^T x [g3|gv]  (accumulates dWc2 and dW3 over all tiles)
     if (issuer) {
-      issue_range(S.mma, kChainDW3, kChainB2, tmem, any_tile);
+      issue_chain_ct<128, 8, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW3, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes, sm_g3v_hi, sm_g3v_lo, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);  // G2 overwrites A2, which this MMA reads
@@ -680,19 +640,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(7);  // G2 epilogue + sync
     // ---- P6: dL/dA1 = G2 x W2 ; dW2 += G2^T x A1 ; dB2 += G2^T x [X|1]
     if (issuer) {
-#ifdef WB_TC_INTERLEAVE
-      // the three chains write different accumulators: issue them round-robin so that consecutive MMAs are independent
-#pragma unroll 4
-      for (int i = 0; i < 24; i++) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const MmaEntry e = S.mma[kChainB2 + c * 24 + i];
-          tc::mma_tf32(tmem + e.tmem_col, e.da, e.db, e.idesc, e.acc_mode == 1u || (e.acc_mode == 2u && any_tile));
-        }
-      }
-#else
-      issue_range(S.mma, kChainB2, kChainDW1, tmem, any_tile);
-#endif
+      issue_chain_ct<64, 64, kKMajor, kS, kMnMajor, kHid, 8>(tmem + kColB2, sm_act_hi + 4 * kBlkBytes, sm_act_lo + 4 * kBlkBytes, sm_w2_hi, sm_w2_lo, false);
+      issue_chain_ct<64, 64, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW2, sm_act_hi + 4 * kBlkBytes, sm_act_lo + 4 * kBlkBytes, sm_act_hi, sm_act_lo, any_tile);
+      issue_chain_ct<64, 16, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDB2, sm_act_hi + 4 * kBlkBytes, sm_act_lo + 4 * kBlkBytes, sm_xt_hi, sm_xt_lo, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -732,7 +682,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(9);  // P7: G1 / Gc1 epilogue + sync
     // ---- P8: [G1|Gc1]^T x [X|1]  (accumulates dW1, db1, dWc1, dbc1)
     if (issuer) {
-      issue_range(S.mma, kChainDW1, kMmaEntries, tmem, any_tile);
+      issue_chain_ct<128, 16, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW1, sm_act_hi, sm_act_lo, sm_xt_hi, sm_xt_lo, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);  // the next tile overwrites XT and ACT
