@@ -169,9 +169,10 @@ constexpr int kBlk = kS * 32;    // floats in one 32-feature block of a 64-row t
 constexpr int kTcThreads = 288;
 
 struct __align__(1024) TcSmem {
-  float xt_hi[kBlk], xt_lo[kBlk];            // [X(12) | 1 | 0 0 0] per sample
-  float act_hi[6 * kBlk], act_lo[6 * kBlk];  // blocks 0-1: A1 -> G1, 2-3: C1 -> Gc1, 4-5: A2 -> G2
-  float g3v_hi[kBlk], g3v_lo[kBlk];          // [g3(4) | gv | 0 0 0] per sample
+  // nine 32-feature blocks per part, contiguous so that neighbouring blocks can be read as ONE wider operand:
+  //   block 0     features 0..15: [X(12) | 1 | 0 0 0], features 16..23: [g3(4) | gv | 0 0 0] (the spare half of the X block)
+  //   blocks 1-2  A1 -> G1,   blocks 3-4  C1 -> Gc1,   blocks 5-6  A2,   blocks 7-8  G2 (its own buffer: dW3 may still read A2)
+  float xa_hi[9 * kBlk], xa_lo[9 * kBlk];
   float w2_hi[2 * kBlk], w2_lo[2 * kBlk];    // rows = o (64), features = i (64)
   float w1_hi[128 * 32], w1_lo[128 * 32];    // rows = [W1 o | Wc1 o] (128), features = [i(12) | bias | 0 0 0]
   float w3[kAct * kHid], wc2[kHid], b2[kHid], b3[kAct], bc2[4];
@@ -182,7 +183,9 @@ struct __align__(1024) TcSmem {
 };
 
 // TMEM column map (fp32 columns)
-constexpr uint32_t kColF1 = 0, kColF2 = 128, kColB2 = 192, kColDW2 = 256, kColDB2 = 320, kColDW1 = 336, kColDW3 = 352;
+// kColDW2: 96 columns = G2^T x [X | 1 | .. | A1]: column 12 = db2, columns 32..95 = dW2 (one chain, the operands share A = G2)
+constexpr uint32_t kColF1 = 0, kColF2 = 128, kColB2 = 192, kColDW2 = 256, kColDW1 = 352, kColDW3 = 368;
+constexpr int kG3vFeature = 16;  // first feature of [g3 | gv] inside block 0
 constexpr uint32_t kTmemCols = 512;
 
 enum : int { kKMajor = 0, kMnMajor = 1 };
@@ -273,6 +276,12 @@ __device__ unsigned long long g_tc_prof[16];
 __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p, const TcConsts gc) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+  float* const xt_hi = S.xa_hi;               // block 0
+  float* const xt_lo = S.xa_lo;
+  float* const act_hi = S.xa_hi + kBlk;       // blocks 1..6: A1 | C1 | A2 (G1 / Gc1 overwrite A1 / C1)
+  float* const act_lo = S.xa_lo + kBlk;
+  float* const g2_hi = S.xa_hi + 7 * kBlk;    // blocks 7..8
+  float* const g2_lo = S.xa_lo + 7 * kBlk;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool epi = warp < 8;                       // epilogue warps: TMEM sub-partition warp % 4 (lanes 32(w%4)..+31)
   const int half = (warp >> 2) & 1;                // which half of every column block this warp owns (see header comment)
@@ -295,11 +304,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     S.w1_hi[i] = 0.f;
     S.w1_lo[i] = 0.f;
   }
-  for (int i = tid; i < kBlk; i += kTcThreads) {
-    S.xt_hi[i] = 0.f;
-    S.xt_lo[i] = 0.f;
-    S.g3v_hi[i] = 0.f;
-    S.g3v_lo[i] = 0.f;
+  for (int i = tid; i < 9 * kBlk; i += kTcThreads) {  // (every operand the MMAs may touch is finite from the start)
+    S.xa_hi[i] = 0.f;
+    S.xa_lo[i] = 0.f;
   }
   __syncthreads();
   for (int i = tid; i < kHid * kHid; i += kTcThreads) {
@@ -334,9 +341,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   const uint32_t tmem = S.tmem_slot;
   const uint32_t tmem_warp = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   // shared-window byte addresses of the operand tiles (identical in every thread: the MMA descriptors derive from them by constants)
-  const uint32_t sm_xt_hi = tc::smem_u32(S.xt_hi), sm_xt_lo = tc::smem_u32(S.xt_lo);
-  const uint32_t sm_act_hi = tc::smem_u32(S.act_hi), sm_act_lo = tc::smem_u32(S.act_lo);
-  const uint32_t sm_g3v_hi = tc::smem_u32(S.g3v_hi), sm_g3v_lo = tc::smem_u32(S.g3v_lo);
+  const uint32_t sm_xt_hi = tc::smem_u32(xt_hi), sm_xt_lo = tc::smem_u32(xt_lo);
+  const uint32_t sm_act_hi = tc::smem_u32(act_hi), sm_act_lo = tc::smem_u32(act_lo);
+  const uint32_t sm_g2_hi = tc::smem_u32(g2_hi), sm_g2_lo = tc::smem_u32(g2_lo);
   const uint32_t sm_w2_hi = tc::smem_u32(S.w2_hi), sm_w2_lo = tc::smem_u32(S.w2_lo);
   const uint32_t sm_w1_hi = tc::smem_u32(S.w1_hi), sm_w1_lo = tc::smem_u32(S.w1_lo);
   constexpr uint32_t kBlkBytes = kBlk * 4;
@@ -396,8 +403,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
         float h, l;
         tc::split_tf32(x_next[q], h, l);
         const int off = tile_off_b32(i >> 4, i & 15, kS);
-        S.xt_hi[off] = h;
-        S.xt_lo[off] = l;
+        xt_hi[off] = h;
+        xt_lo[off] = l;
       }
     }
     const float a_cur[2] = {a_next[0], a_next[1]}, lp_cur[2] = {lp_next[0], lp_next[1]};
@@ -425,8 +432,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     unsigned mask1[2] = {0u, 0u};  // half 0: A1 < 0 per column; half 1: C1 < 0 per column
     float value = 0.f;
     if (epi) {
-      float* hi_t = S.act_hi + half * 2 * kBlk;
-      float* lo_t = S.act_lo + half * 2 * kBlk;
+      float* hi_t = act_hi + half * 2 * kBlk;
+      float* lo_t = act_lo + half * 2 * kBlk;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         float v[32];
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       if (is_sample) {
         if (grad) {
 #pragma unroll
-          for (int u = 0; u < 32; u += 8) store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c0 + u, v + u);
+          for (int u = 0; u < 32; u += 8) store_unit(act_hi + 4 * kBlk, act_lo + 4 * kBlk, s_loc, c0 + u, v + u);
         }
         *reinterpret_cast<float4*>(&S.mu_part[half][s_loc][0]) = make_float4(part[0], part[1], part[2], part[3]);
       }
@@ -595,25 +602,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     }
     if (is_sample && half == 1) {
       const float u[8] = {g3[0], g3[1], g3[2], g3[3], gv, 0.f, 0.f, 0.f};
-      store_unit(S.g3v_hi, S.g3v_lo, s_loc, 0, u);
+      store_unit(xt_hi, xt_lo, s_loc, kG3vFeature, u);
     }
-    tc::fence_proxy_async_smem();
-    tc::fence_before_thread_sync();
-    __syncthreads();
-    tc::fence_after_thread_sync();
-
-    TC_MARK(5);  // surrogate gradient + g3v staging + sync
-    // ---- P5: [C1|A2]^T x [g3|gv]  (accumulates dWc2 and dW3 over all tiles)
-    if (issuer) {
-      issue_chain_ct<128, 8, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW3, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes, sm_g3v_hi, sm_g3v_lo, any_tile);
-      tc::mma_commit(&S.mbar);
-    }
-    if (epi) tc::mbar_wait(&S.mbar, phase);  // G2 overwrites A2, which this MMA reads
-    phase ^= 1;
-    __syncwarp();
-    tc::fence_after_thread_sync();
-    TC_MARK(6);  // P5: dW3 MMA + wait
-    // dL/dz2 = (W3^T g3) * leaky'(z2) for the half's 32 columns (sum over k from 0, Matrix.Multiply order)
+    TC_MARK(5);  // surrogate gradient + g3v staging
+    // dL/dz2 = (W3^T g3) * leaky'(z2) for the half's 32 columns (sum over k from 0, Matrix.Multiply order).  G2 has its own
+    // tile, so nothing here waits for the dW3 product (which reads A2): it is issued together with the G2 products below.
     if (epi) {
       const int c0 = half * 32;
 #pragma unroll
@@ -629,7 +622,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
           sum = fmaf(S.w3[3 * kHid + o], g3[3], sum);
           v[j] = sum * (((maskA2 >> (c + j)) & 1u) ? 0.2f : 1.0f);
         }
-        if (is_sample) store_unit(S.act_hi + 4 * kBlk, S.act_lo + 4 * kBlk, s_loc, c0 + c, v);  // G2 overwrites A2
+        if (is_sample) store_unit(g2_hi, g2_lo, s_loc, c0 + c, v);
       }
     }
     tc::fence_proxy_async_smem();
@@ -638,11 +631,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     tc::fence_after_thread_sync();
 
     TC_MARK(7);  // G2 epilogue + sync
-    // ---- P6: dL/dA1 = G2 x W2 ; dW2 += G2^T x A1 ; dB2 += G2^T x [X|1]
+    // ---- P5/P6 in one batch: [C1|A2]^T x [g3|gv] (dWc2, dW3) ; dL/dA1 = G2 x W2 ; G2^T x [X | 1 | .. | A1] (db2, dW2)
     if (issuer) {
-      issue_chain_ct<64, 64, kKMajor, kS, kMnMajor, kHid, 8>(tmem + kColB2, sm_act_hi + 4 * kBlkBytes, sm_act_lo + 4 * kBlkBytes, sm_w2_hi, sm_w2_lo, false);
-      issue_chain_ct<64, 64, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW2, sm_act_hi + 4 * kBlkBytes, sm_act_lo + 4 * kBlkBytes, sm_act_hi, sm_act_lo, any_tile);
-      issue_chain_ct<64, 16, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDB2, sm_act_hi + 4 * kBlkBytes, sm_act_lo + 4 * kBlkBytes, sm_xt_hi, sm_xt_lo, any_tile);
+      issue_chain_ct<128, 8, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW3, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes,
+                                                            sm_xt_hi + kG3vFeature * 4, sm_xt_lo + kG3vFeature * 4, any_tile);
+      issue_chain_ct<64, 64, kKMajor, kS, kMnMajor, kHid, 8>(tmem + kColB2, sm_g2_hi, sm_g2_lo, sm_w2_hi, sm_w2_lo, false);
+      issue_chain_ct<64, 96, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW2, sm_g2_hi, sm_g2_lo, sm_xt_hi, sm_xt_lo, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -653,8 +647,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(8);  // P6: B2 / dW2 / dB2 MMA + wait
     // ---- P7: half 0: G1 = dL/dA1 * leaky'(z1) -> overwrites A1; half 1: Gc1 = (Wc2^T gv) * leaky'(zc1) -> overwrites C1
     if (epi) {
-      float* hi_t = S.act_hi + half * 2 * kBlk;
-      float* lo_t = S.act_lo + half * 2 * kBlk;
+      float* hi_t = act_hi + half * 2 * kBlk;
+      float* lo_t = act_lo + half * 2 * kBlk;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         float v[32];
@@ -709,7 +703,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 #pragma unroll 1
       for (int c = 0; c < 64; c += 16) {
         float v[16];
-        tc::tmem_ld_x16(tmem_warp + kColDW2 + c, v);
+        tc::tmem_ld_x16(tmem_warp + kColDW2 + 32 + c, v);
         tc::tmem_ld_wait();
         if (is_sample)
 #pragma unroll
@@ -717,7 +711,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       }
       {
         float v[16];
-        tc::tmem_ld_x16(tmem_warp + kColDB2, v);
+        tc::tmem_ld_x16(tmem_warp + kColDW2, v);
         tc::tmem_ld_wait();
         if (is_sample) out[kOffB2 + s_loc] = v[12];
       }
