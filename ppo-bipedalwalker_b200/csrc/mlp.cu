@@ -646,17 +646,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ grads,
                                                                        ExchPeers peers, int rank, int world, uint32_t epoch, uint32_t* status,
                                                                        AdamParams adam, int do_adam) {
-  // 4 threads per float4 of the slice: each sums every 4th per-CTA partial (independent loads in flight), then the four
+  // kExchLanes threads per float4 of the slice: each sums every kExchLanes-th per-CTA partial (<= 10 independent loads in flight
+  // per thread, 97 CTAs: the 3.6 MB of partials are read at memory speed instead of as 13 CTAs' dependent chains), then the
   // partial sums are combined pairwise by shuffles -- a fixed order, so the result is deterministic
-  const int part = threadIdx.x & 3;
-  const int i4 = blockIdx.x * (kExchThreads / 4) + (threadIdx.x >> 2);  // float4 index inside the gradient buffer
+  const int part = threadIdx.x & (kExchLanes - 1);
+  const int i4 = blockIdx.x * (kExchThreads / kExchLanes) + (threadIdx.x / kExchLanes);  // float4 index inside the gradient buffer
   const bool in = i4 < kGradFloats / 4;
   const int par = (int)(epoch & 1u);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (in) {
     const float4* p4 = reinterpret_cast<const float4*>(partials) + i4;
-#pragma unroll 4
-    for (int q = part; q < nparts; q += 4) {
+#pragma unroll 10
+    for (int q = part; q < nparts; q += kExchLanes) {
       const float4 v = p4[(size_t)q * (kGradFloats / 4)];
       acc.x += v.x;
       acc.y += v.y;
@@ -665,7 +666,7 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
     }
   }
 #pragma unroll
-  for (int m = 1; m <= 2; m <<= 1) {
+  for (int m = 1; m < kExchLanes; m <<= 1) {
     acc.x += __shfl_xor_sync(0xFFFFFFFFu, acc.x, m);
     acc.y += __shfl_xor_sync(0xFFFFFFFFu, acc.y, m);
     acc.z += __shfl_xor_sync(0xFFFFFFFFu, acc.z, m);
@@ -678,8 +679,8 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
     // is a no-op (no store, no Adam) until the host has seen the status word (wb_comm_status / wb_ppo_train_dev refuse)
     if (__syncthreads_or(threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(status) != 0u)) return;  // (CTA-uniform)
     if (in) {
-      // push my slice into slot [par][rank] of every rank (NVLink stores; r == rank is local); the 4 lanes of an element share the peers
-      for (int r = part; r < world; r += 4) reinterpret_cast<float4*>(peers.base[r] + exch_slot_offset(par, rank))[i4] = acc;
+      // push my slice into slot [par][rank] of every rank (NVLink stores; r == rank is local); the lanes of an element share the peers
+      for (int r = part; r < world; r += kExchLanes) reinterpret_cast<float4*>(peers.base[r] + exch_slot_offset(par, rank))[i4] = acc;
     }
     __threadfence_system();
     __syncthreads();

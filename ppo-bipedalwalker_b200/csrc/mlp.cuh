@@ -77,8 +77,9 @@ cudaError_t launch_returns(const float* rewards, const float* values, int n, flo
 
 // ---- exchange buffer of the fused reduce + all-reduce (one allocation per rank, shared with the peers through CUDA IPC)
 constexpr int kExchMaxWorld = 8;
-constexpr int kExchThreads = 512;
-constexpr int kExchCtas = (kGradFloats / 4 + kExchThreads / 4 - 1) / (kExchThreads / 4);  // 13 slices of 128 float4 (4 threads per float4)
+constexpr int kExchThreads = 256;
+constexpr int kExchLanes = 16;   // threads per float4 of the gradient buffer: each sums every 16th per-CTA partial
+constexpr int kExchCtas = (kGradFloats / 4 + kExchThreads / kExchLanes - 1) / (kExchThreads / kExchLanes);  // 97 slices of 16 float4
 struct ExchPeers {
   float* base[kExchMaxWorld];  // every rank's exchange buffer as seen from this process
 };

@@ -287,9 +287,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   const int half = (warp >> 2) & 1;                // which half of every column block this warp owns (see header comment)
   const bool is_sample = epi && lane < 16;         // lanes 32w..32w+15 hold rows 16w..16w+15 of an M=64 accumulator
   const int s_loc = (warp & 3) * 16 + (lane & 15);
+  const int lh = lane >> 4;                        // which half of the warp's column range this lane owns (16x32bx2 loads)
   const bool issuer = tid == 256;                  // lane 0 of the dedicated issuer warp: tcgen05.mma / commit
   const bool grad = p.mode == kModeGrad;
 
+#ifdef WB_TC_PROFILE
+  long long tc_t0;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc_t0)::"memory");
+#endif
   if (warp == 0) tc::tmem_alloc(&S.tmem_slot, kTmemCols);
   if (tid == 0) {
     tc::mbar_init(&S.mbar, 1);
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   unsigned long long tc_acc[12] = {};
   long long tc_t;
   asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc_t)::"memory");
+  if (tid == 0) atomicAdd(&g_tc_prof[12], (unsigned long long)(tc_t - tc_t0));  // prologue: TMEM, weight tiles, first prefetch
 #endif
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int s0 = tile * kS;
@@ -429,32 +435,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(1);  // P1: F1 MMA + wait
     // ---- P2: half 0: A1 = leaky(F1[:, 0:64]); half 1: C1 = leaky(F1[:, 64:128]), V = Wc2 . C1 + bc2 (left to right).
     //      The sign masks (LeakyReLU derivative) stay with the half that owns the columns.
-    unsigned mask1[2] = {0u, 0u};  // half 0: A1 < 0 per column; half 1: C1 < 0 per column
+    //      Every thread owns sample s_loc and 32 of its half's 64 columns (threads 0..15 the first 32, threads 16..31 the
+    //      next 32: 16x32bx2 loads), so all 32 lanes of the eight epilogue warps do useful work.
+    unsigned mask1 = 0u;  // my 32 columns: A1 < 0 (half 0) / C1 < 0 (half 1)
     float value = 0.f;
     if (epi) {
       float* hi_t = act_hi + half * 2 * kBlk;
       float* lo_t = act_lo + half * 2 * kBlk;
+      const int cb = lh * 32;
+      float v[32];
+      tc::tmem_ld_16x2_x32(tmem_warp + kColF1 + half * 64, v);
+      tc::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        float v[32];
-        tc::tmem_ld_x32(tmem_warp + kColF1 + half * 64 + c, v);
-        tc::tmem_ld_wait();
-        unsigned m = 0u;
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          v[j] = tc_leaky(v[j]);
-          m |= (v[j] < 0.0f ? 1u : 0u) << j;
-        }
-        mask1[c >> 5] = m;
-        if (half == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) value = fmaf(v[j], S.wc2[c + j], value);
-        }
-        if (is_sample) {
-#pragma unroll
-          for (int u = 0; u < 32; u += 8) store_unit(hi_t, lo_t, s_loc, c + u, v + u);
-        }
+      for (int j = 0; j < 32; j++) {
+        v[j] = tc_leaky(v[j]);
+        mask1 |= (v[j] < 0.0f ? 1u : 0u) << j;
       }
+      if (half == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) value = fmaf(v[j], S.wc2[cb + j], value);
+      }
+#pragma unroll
+      for (int u = 0; u < 32; u += 8) store_unit(hi_t, lo_t, s_loc, cb + u, v + u);
+      value += __shfl_xor_sync(0xFFFFFFFFu, value, 16);  // the two column halves of the sample's dot product
       value += S.bc2[0];
     }
     tc::fence_proxy_async_smem();
@@ -475,27 +478,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     TC_MARK(3);  // P3: F2 MMA + wait
     // ---- P4: each half: A2 = leaky(F2 + b2) for its 32 columns and its partial W3 . A2; the partials meet in shared memory
-    unsigned maskA2 = 0u;  // own 32 columns
+    unsigned maskA2 = 0u;  // my 16 columns
     if (epi) {
-      const int c0 = half * 32;
-      float v[32];
+      const int c0 = half * 32 + lh * 16;
+      float v[16];
       float part[kAct] = {0.f, 0.f, 0.f, 0.f};
-      tc::tmem_ld_x32(tmem_warp + kColF2 + c0, v);
+      tc::tmem_ld_16x2_x16(tmem_warp + kColF2 + half * 32, v);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
+      for (int j = 0; j < 16; j++) {
         v[j] = tc_leaky(v[j] + S.b2[c0 + j]);
         maskA2 |= (v[j] < 0.0f ? 1u : 0u) << j;
 #pragma unroll
         for (int k = 0; k < kAct; k++) part[k] = fmaf(v[j], S.w3[k * kHid + c0 + j], part[k]);
       }
-      if (is_sample) {
-        if (grad) {
+      if (grad) {
 #pragma unroll
-          for (int u = 0; u < 32; u += 8) store_unit(act_hi + 4 * kBlk, act_lo + 4 * kBlk, s_loc, c0 + u, v + u);
-        }
-        *reinterpret_cast<float4*>(&S.mu_part[half][s_loc][0]) = make_float4(part[0], part[1], part[2], part[3]);
+        for (int u = 0; u < 16; u += 8) store_unit(act_hi + 4 * kBlk, act_lo + 4 * kBlk, s_loc, c0 + u, v + u);
       }
+#pragma unroll
+      for (int k = 0; k < kAct; k++) part[k] += __shfl_xor_sync(0xFFFFFFFFu, part[k], 16);
+      if (lh == 0) *reinterpret_cast<float4*>(&S.mu_part[half][s_loc][0]) = make_float4(part[0], part[1], part[2], part[3]);
     }
     __syncthreads();
     float mu[kAct] = {0.f, 0.f, 0.f, 0.f};
@@ -577,24 +580,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       g3[1] = k0 == 0 ? part[1] : o1;
       g3[2] = k0 == 0 ? o0 : part[0];
       g3[3] = k0 == 0 ? o1 : part[1];
-      if (valid) {
+      // both lane halves of a sample carry the same g3 / gv (each needs them for its columns of G2 / Gc1); the per-sample sums are
+      // kept by the first half only (valid: lanes 0..15)
+      if (live) {
         if (half == 1) gv = (2.0f * (value - ret_cur)) / p.batch_size;
         if (skip) {
 #pragma unroll
           for (int k = 0; k < kAct; k++) g3[k] = 0.f;
           gv = 0.f;
-          if (half == 0) skipped += 1.0f;
-        } else if (half == 0) {
+          if (valid && half == 0) skipped += 1.0f;
+        } else if (valid && half == 0) {
           lossA += (((g3[0] + g3[1]) + g3[2]) + g3[3]) / (float)kAct;
-        } else {
+        } else if (valid) {
           lossV += gv;
         }
 #pragma unroll
         for (int k = 0; k < kAct; k++) {
           g3[k] = g3[k] * (1.0f - (mu[k] * mu[k]));  // TanhLayer.FeedBack
-          if (half == 0) db3_acc[k] += g3[k];
+          if (valid && half == 0) db3_acc[k] += g3[k];
         }
-        if (half == 1) dbc2_acc += gv;
+        if (valid && half == 1) dbc2_acc += gv;
       } else {
 #pragma unroll
         for (int k = 0; k < kAct; k++) g3[k] = 0.f;
@@ -608,9 +613,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     // dL/dz2 = (W3^T g3) * leaky'(z2) for the half's 32 columns (sum over k from 0, Matrix.Multiply order).  G2 has its own
     // tile, so nothing here waits for the dW3 product (which reads A2): it is issued together with the G2 products below.
     if (epi) {
-      const int c0 = half * 32;
+      const int c0 = half * 32 + lh * 16;
 #pragma unroll
-      for (int c = 0; c < 32; c += 8) {
+      for (int c = 0; c < 16; c += 8) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -622,7 +627,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
           sum = fmaf(S.w3[3 * kHid + o], g3[3], sum);
           v[j] = sum * (((maskA2 >> (c + j)) & 1u) ? 0.2f : 1.0f);
         }
-        if (is_sample) store_unit(g2_hi, g2_lo, s_loc, c0 + c, v);
+        store_unit(g2_hi, g2_lo, s_loc, c0 + c, v);
       }
     }
     tc::fence_proxy_async_smem();
@@ -649,24 +654,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     if (epi) {
       float* hi_t = act_hi + half * 2 * kBlk;
       float* lo_t = act_lo + half * 2 * kBlk;
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        float v[32];
-        if (half == 0) {
-          tc::tmem_ld_x32(tmem_warp + kColB2 + c, v);
-          tc::tmem_ld_wait();
-        }
-        const unsigned m = mask1[c >> 5];
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float slope = ((m >> j) & 1u) ? 0.2f : 1.0f;
-          v[j] = (half == 0 ? v[j] : (0.0f + S.wc2[c + j] * gv)) * slope;
-        }
-        if (is_sample) {
-#pragma unroll
-          for (int u = 0; u < 32; u += 8) store_unit(hi_t, lo_t, s_loc, c + u, v + u);
-        }
+      const int cb = lh * 32;  // my 32 columns (the ones mask1 describes)
+      float v[32];
+      if (half == 0) {
+        tc::tmem_ld_16x2_x32(tmem_warp + kColB2, v);
+        tc::tmem_ld_wait();
       }
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const float slope = ((mask1 >> j) & 1u) ? 0.2f : 1.0f;
+        v[j] = (half == 0 ? v[j] : (0.0f + S.wc2[cb + j] * gv)) * slope;
+      }
+#pragma unroll
+      for (int u = 0; u < 32; u += 8) store_unit(hi_t, lo_t, s_loc, cb + u, v + u);
     }
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
@@ -739,27 +739,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
         }
       }
     }
-    // db3, dbc2 and the loss sums: fixed-order block reduction of per-thread partials
+    // db3, dbc2 and the loss sums: per-thread partials -> butterfly inside every warp -> the nine warp sums added in warp order
+    // (a fixed order: deterministic), all eight quantities in ONE pass
+    float mine[8] = {db3_acc[0], db3_acc[1], db3_acc[2], db3_acc[3], dbc2_acc, lossV, lossA, skipped};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) mine[q] += __shfl_xor_sync(0xFFFFFFFFu, mine[q], m);
+    }
+    __syncthreads();  // (S.red is free: every warp is past the tile loop)
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) S.red[warp * 8 + q] = mine[q];
+    }
     __syncthreads();
-    for (int pass = 0; pass < 8; pass++) {
-      const float mine = pass < 4 ? db3_acc[pass] : pass == 4 ? dbc2_acc : pass == 5 ? lossV : pass == 6 ? lossA : skipped;
-      S.red[tid] = mine;
-      if (tid < 512 - kTcThreads) S.red[kTcThreads + tid] = 0.f;
-      __syncthreads();
-      for (int w = 256; w > 0; w >>= 1) {
-        if (tid < w) S.red[tid] += S.red[tid + w];
-        __syncthreads();
-      }
-      if (tid == 0) {
-        const int dst = pass < 4 ? kOffB3 + pass : pass == 4 ? kOffBc2 : kTotalParams + (pass - 5);
-        out[dst] = S.red[0];
-      }
-      __syncthreads();
+    if (tid < 8) {
+      float sum = 0.f;
+      for (int w = 0; w < kTcThreads / 32; w++) sum += S.red[w * 8 + tid];
+      const int dst = tid < 4 ? kOffB3 + tid : tid == 4 ? kOffBc2 : kTotalParams + (tid - 5);
+      out[dst] = sum;
     }
   }
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+#ifdef WB_TC_PROFILE
+  if (tid == 0) {
+    long long now_;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_)::"memory");
+    atomicAdd(&g_tc_prof[13], (unsigned long long)(now_ - tc_t));  // after the tile loop: TMEM read-out, reductions
+  }
+#endif
 }
 
 #ifdef WB_TC_PROFILE

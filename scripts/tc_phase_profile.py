@@ -25,3 +25,4 @@ ctas = int(out[11]); tiles = 1024 * K
 tot = sum(int(out[i]) for i in range(11))
 print(f"cycles per tile (thread 0 of each CTA), {ctas} CTA-launches, {tiles} tiles: total {tot / tiles:.0f}")
 for i, nm in enumerate(names): print(f"  {nm:32s} {int(out[i]) / tiles:8.0f}  {100 * int(out[i]) / tot:5.1f}%")
+print(f"per CTA-launch: prologue {int(out[12]) / ctas:.0f} cycles, after the tile loop {int(out[13]) / ctas:.0f} cycles, tiles {tot / ctas:.0f} cycles")
