@@ -34,6 +34,8 @@ struct wb_policy {
   uint32_t* h_comm_status = nullptr;  // mapped pinned host word: set by reduce_exchange_kernel when a peer never arrived
   uint32_t* d_comm_status = nullptr;  // its device alias
   double* d_norm_stats = nullptr;     // [2][kNormCtas] partial sums of PPOAgent.Normalize (wb_normalize_advantages_dev)
+  uint32_t* d_grid_sync = nullptr;    // arrival counter of the gradient kernel's grid barrier (fused single-process tail)
+  uint32_t grid_sync_target = 0;
   ExchPeers peers{};
   void* opened[kExchMaxWorld] = {};  // IPC mappings to close
   int comm_rank = -1, comm_world = 0;
@@ -206,6 +208,8 @@ int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t*
   if (e == cudaSuccess) e = cudaMalloc(&p->d_v, sizeof(float) * p->n_total);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_partials, sizeof(float) * p->grad_floats * (size_t)(2 * p->sm_count));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_norm_stats, sizeof(double) * 2 * kNormCtas);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_grid_sync, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(p->d_grid_sync, 0, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaHostAlloc(&p->h_comm_status, sizeof(uint32_t), cudaHostAllocMapped);
   if (e == cudaSuccess) {
     *p->h_comm_status = 0;
@@ -234,6 +238,7 @@ int32_t wb_policy_destroy(wb_policy* p) {
   cudaFree(p->d_exch);
   if (p->h_comm_status) cudaFreeHost(p->h_comm_status);
   cudaFree(p->d_norm_stats);
+  cudaFree(p->d_grid_sync);
   cudaFree(p->d_partials);
   cudaFree(p->d_stage);
   delete p;
@@ -632,9 +637,9 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
   m.returns = returns_dev;
   m.partials = p->d_partials;
   const int grid = grid_of(p, n);
-  WB_CUDA(run_mlp(p, m));
   if (use_generic(p)) {  // any topology: reduction and Adam as separate launches (single rank; data-parallel callers use the NCCL path)
     WB_REQUIRE(p->comm_world < 2, "a connected policy needs the default networks and kernel variant 0 or 1");
+    WB_CUDA(run_mlp(p, m));
     WB_CUDA(reduce_grads(p, grid));
     WB_CUDA(adam_any(p));
     p->launches += 3;
@@ -643,6 +648,21 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
   AdamParams a;
   next_adam_params(p, a);
   const int world = p->comm_world >= 2 ? p->comm_world : 1;
+  if (world == 1 && p->variant == 0 && grid <= p->sm_count) {
+    // ONE launch: the tensor-core gradient kernel reduces its own partials behind a grid barrier and applies Adam (the grid is
+    // persistent, one CTA per SM, so every CTA is resident)
+    FusedTail t{};
+    t.enabled = 1;
+    t.counter = p->d_grid_sync;
+    p->grid_sync_target += (uint32_t)grid;
+    t.target = p->grid_sync_target;
+    t.grads = p->d_grads;
+    t.adam = a;
+    WB_CUDA(launch_mlp_tc(m, grid, p->stream, &t));
+    p->launches += 1;
+    return WB_OK;
+  }
+  WB_CUDA(run_mlp(p, m));
   if (world > 1) p->comm_epoch++;
   WB_CUDA(launch_reduce_exchange(p->d_partials, grid, p->d_grads, p->peers, world > 1 ? p->comm_rank : 0, world, p->comm_epoch,
                                  p->d_comm_status, &a, p->stream));

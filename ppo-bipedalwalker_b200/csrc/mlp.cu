@@ -413,19 +413,6 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
   grads[i] = sum;
 }
 
-// DenseLayer.Adam for one parameter (DenseLayer.cs:125-159; every product and sum individually rounded, as the Matrix operators do)
-__device__ __forceinline__ void adam_update(const AdamParams& a, int i, float g) {
-  const int layer = (i < kOffW2) ? 0 : (i < kOffW3) ? 1 : (i < kActorParams) ? 2 : (i < kOffWc2) ? 3 : 4;
-  const float m = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, a.beta1), g), __fmul_rn(a.beta1, a.m[i]));
-  const float v = __fadd_rn(__fmul_rn(a.beta2, a.v[i]), __fmul_rn(__fsub_rn(1.0f, a.beta2), __fmul_rn(g, g)));
-  a.m[i] = m;
-  a.v[i] = v;
-  const float mhat = __fdiv_rn(m, a.corr1[layer]);
-  const float vhat = __fdiv_rn(v, a.corr2[layer]);
-  const float denom = __fadd_rn(__fsqrt_rn(vhat), a.eps);
-  a.params[i] = __fsub_rn(a.params[i], __fmul_rn(a.alpha, __fdiv_rn(mhat, denom)));
-}
-
 __global__ void adam_kernel(const AdamParams a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kTotalParams) return;

@@ -68,6 +68,32 @@ struct AdamParams {
   float corr1[5], corr2[5];
 };
 
+#ifdef __CUDACC__
+// DenseLayer.Adam for one parameter (DenseLayer.cs:125-159; every product and sum individually rounded, as the Matrix operators do)
+__device__ __forceinline__ void adam_update(const AdamParams& a, int i, float g) {
+  const int layer = (i < kOffW2) ? 0 : (i < kOffW3) ? 1 : (i < kActorParams) ? 2 : (i < kOffWc2) ? 3 : 4;
+  const float m = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, a.beta1), g), __fmul_rn(a.beta1, a.m[i]));
+  const float v = __fadd_rn(__fmul_rn(a.beta2, a.v[i]), __fmul_rn(__fsub_rn(1.0f, a.beta2), __fmul_rn(g, g)));
+  a.m[i] = m;
+  a.v[i] = v;
+  const float mhat = __fdiv_rn(m, a.corr1[layer]);
+  const float vhat = __fdiv_rn(v, a.corr2[layer]);
+  const float denom = __fadd_rn(__fsqrt_rn(vhat), a.eps);
+  a.params[i] = __fsub_rn(a.params[i], __fmul_rn(a.alpha, __fdiv_rn(mhat, denom)));
+}
+#endif
+
+// Tail of the gradient kernel when ONE process trains (no exchange): after a grid-wide barrier (every CTA of the persistent grid is
+// resident: one per SM) each CTA reduces its slice of the per-CTA partials in a fixed order and applies DenseLayer.Adam to it --
+// PPOAgent.Train(Batch) in ONE launch instead of gradient kernel + reduction kernel.
+struct FusedTail {
+  int32_t enabled;
+  uint32_t* counter;   // monotonically increasing arrival counter of the grid barrier
+  uint32_t target;     // value the counter reaches when every CTA of THIS launch has arrived
+  float* grads;        // [kGradFloats] reduced gradient (+ loss sums, skipped)
+  AdamParams adam;
+};
+
 int mlp_grid_for(int n, int sm_count);
 cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_reduce_partials(const float* partials, int nparts, float* grads, cudaStream_t stream);
@@ -155,7 +181,7 @@ cudaError_t launch_reduce_partials_n(const float* partials, int nparts, float* g
 cudaError_t launch_adam_generic(const GenAdamParams& a, cudaStream_t stream);
 
 int tc_grid_for(int n, int sm_count);
-cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream, const FusedTail* tail = nullptr);
 cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M, int N, int K, int a_mn, int b_mn, int passes,
                                 cudaStream_t stream);
 

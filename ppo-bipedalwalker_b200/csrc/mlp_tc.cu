@@ -273,7 +273,7 @@ __device__ unsigned long long g_tc_prof[16];
 #define TC_MARK(k)
 #endif
 
-__global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p, const TcConsts gc) {
+__global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p, const TcConsts gc, const FusedTail tail) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   float* const xt_hi = S.xa_hi;               // block 0
@@ -300,28 +300,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     tc::mbar_init(&S.mbar, 1);
     tc::mbar_fence_init();
   }
-  // ---- weights -> dual-use tiles (once per CTA)
-  for (int i = tid; i < 2 * kBlk; i += kTcThreads) {
-    S.w2_hi[i] = 0.f;
-    S.w2_lo[i] = 0.f;
-  }
-  for (int i = tid; i < 128 * 32; i += kTcThreads) {
-    S.w1_hi[i] = 0.f;
-    S.w1_lo[i] = 0.f;
-  }
-  for (int i = tid; i < 9 * kBlk; i += kTcThreads) {  // (every operand the MMAs may touch is finite from the start)
-    S.xa_hi[i] = 0.f;
-    S.xa_lo[i] = 0.f;
+  // ---- weights -> dual-use tiles (once per CTA).  The activation tiles and the W1 tile are cleared first (16-byte stores): every
+  //      operand element an MMA may read is finite from the start (the rows of a ragged last tile carry zero gradients, and
+  //      0 x garbage would not be 0); the W2 tile is written completely below.
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* xa4h = reinterpret_cast<float4*>(S.xa_hi);
+    float4* xa4l = reinterpret_cast<float4*>(S.xa_lo);
+    for (int i = tid; i < 9 * kBlk / 4; i += kTcThreads) {
+      xa4h[i] = z4;
+      xa4l[i] = z4;
+    }
+    float4* w14h = reinterpret_cast<float4*>(S.w1_hi);
+    float4* w14l = reinterpret_cast<float4*>(S.w1_lo);
+    for (int i = tid; i < 128 * 32 / 4; i += kTcThreads) {
+      w14h[i] = z4;
+      w14l[i] = z4;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < kHid * kHid; i += kTcThreads) {
-    const int o = i >> 6, in = i & 63;
-    float h, l;
-    tc::split_tf32(p.params[kOffW2 + i], h, l);
+  // W2: four consecutive inputs of one output row per thread (one 16-byte load, one 16-byte store per part: the four share a unit)
+#pragma unroll 2
+  for (int i = tid; i < kHid * kHid / 4; i += kTcThreads) {
+    const int o = i >> 4, in = (i & 15) * 4;
+    const float4 w = *reinterpret_cast<const float4*>(p.params + kOffW2 + o * kHid + in);
+    float4 h, l;
+    tc::split_tf32(w.x, h.x, l.x);
+    tc::split_tf32(w.y, h.y, l.y);
+    tc::split_tf32(w.z, h.z, l.z);
+    tc::split_tf32(w.w, h.w, l.w);
     const int off = tile_off_b32(o, in, kHid);
-    S.w2_hi[off] = h;
-    S.w2_lo[off] = l;
+    *reinterpret_cast<float4*>(S.w2_hi + off) = h;
+    *reinterpret_cast<float4*>(S.w2_lo + off) = l;
   }
+#pragma unroll 3
   for (int i = tid; i < 128 * 13; i += kTcThreads) {
     const int r = i / 13, f = i % 13;  // f < 12: weight, f == 12: bias
     const float w = (r < kHid) ? (f < 12 ? p.params[kOffW1 + r * kIn + f] : p.params[kOffB1 + r])
@@ -763,6 +775,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+  if (grad && tail.enabled) {
+    // ---- grid barrier (all CTAs resident), then this CTA's slice of the reduction + Adam
+    __threadfence();  // my partial is visible device-wide before I arrive
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(tail.counter, 1u);
+      uint32_t seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tail.counter) : "memory");
+      } while ((int32_t)(seen - tail.target) < 0);
+    }
+    __syncthreads();
+    const int per = (kGradFloats + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * per;
+    const int hi = min(lo + per, kGradFloats);
+    constexpr int kLanesPer = 8;  // threads per element: each sums every 8th partial, then a butterfly (fixed order: deterministic)
+    const int part = tid & (kLanesPer - 1);
+    for (int base = lo; base < hi; base += kTcThreads / kLanesPer) {  // (uniform trip count: the shuffles below are unconditional)
+      const int e = base + (tid / kLanesPer);
+      const bool in = e < hi;
+      float acc = 0.f;
+      if (in) {
+#pragma unroll 4
+        for (int q = part; q < (int)gridDim.x; q += kLanesPer) acc += __ldcg(p.partials + (size_t)q * kGradFloats + e);
+      }
+#pragma unroll
+      for (int m = 1; m < kLanesPer; m <<= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, m);
+      if (in && part == 0) {
+        tail.grads[e] = acc;
+        if (e < kTotalParams) adam_update(tail.adam, e, acc);
+      }
+    }
+  }
 #ifdef WB_TC_PROFILE
   if (tid == 0) {
     long long now_;
@@ -789,7 +834,7 @@ int tc_grid_for(int n, int sm_count) {
   return ntiles < sm_count ? (ntiles > 0 ? ntiles : 1) : sm_count;
 }
 
-cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream) {
+cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream, const FusedTail* tail) {
   // opt in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute (a process may drive several GPUs)
   static bool configured[64] = {};
   int dev = 0;
@@ -806,7 +851,9 @@ cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream) {
   gc.upper = 1.0f + p.epsilon;
   gc.lower = 1.0f - p.epsilon;
   gc.variance = gc.stdv * gc.stdv;
-  ppo_tc_kernel<<<grid, kTcThreads, sizeof(TcSmem), stream>>>(p, gc);
+  FusedTail t{};
+  if (tail) t = *tail;
+  ppo_tc_kernel<<<grid, kTcThreads, sizeof(TcSmem), stream>>>(p, gc, t);
   return cudaGetLastError();
 }
 

@@ -352,6 +352,33 @@ def test_the_three_policy_kernels_agree_on_the_default_networks(gpu, O):
         assert rel_err(grads[variant], ref) < 1e-4, variant
 
 
+def test_single_launch_train_step_matches_gradient_then_adam(gpu, O):
+    """wb_ppo_train_dev on one process runs PPOAgent.Train(Batch) as ONE launch (the tensor-core kernel reduces its partials behind
+    a grid barrier and applies Adam); the result must equal wb_ppo_grad_dev + wb_adam_step and track the oracle, for a grid of one
+    CTA (n = 64), a partial grid (n = 5000) and the full persistent grid (n = 65536), three steps each."""
+    import torch
+    from ppo_bipedalwalker_b200._lib import check, lib, ptr
+    for n in (64, 5000, 65536):
+        fused, actor, critic, ohp = make_pair(gpu, O, 31, n, variant=0)
+        split, _, _, _ = make_pair(gpu, O, 31, n, variant=0)
+        rng = np.random.default_rng(n)
+        for step in range(3):
+            batch = synth_batch(rng, actor, n, critic_flat=critic.get_params())
+            dev = [torch.from_numpy(x).cuda() for x in batch]
+            check(lib().wb_ppo_train_dev(fused._h, n, *[ptr(t) for t in dev]))
+            check(lib().wb_ppo_grad_dev(split._h, n, *[ptr(t) for t in dev]))
+            check(lib().wb_adam_step(split._h))
+            fused.sync()
+            split.sync()
+            O.ppo_train_batch(actor, critic, ohp, *batch, optimise=True)
+            for net_f, net_s, net_o in ((fused.actor, split.actor, actor), (fused.critic, split.critic, critic)):
+                np.testing.assert_allclose(net_f.get_flat(), net_s.get_flat(), rtol=0, atol=2e-6)   # same gradients, other summation order
+                np.testing.assert_allclose(net_f.get_flat(), net_o.get_params(), rtol=0, atol=3e-5)
+                assert rel_err(net_f.get_grads(), net_s.get_grads()) < 1e-5
+        _, _, iters = fused.actor.get_adam()
+        assert list(iters) == [3, 3, 3]
+
+
 def test_topologies_outside_the_kernels_fail_loudly(gpu):
     with pytest.raises(gpu.WalkerB200Error):  # wider than the 128 the kernels cover: refused, never a silent fallback
         gpu.PPOAgent(actor="Input |256| (ReLU) |4| (TanH) Output")
