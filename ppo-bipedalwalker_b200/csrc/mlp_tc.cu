@@ -149,24 +149,28 @@ cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M,
 // ppo_tc_kernel: the fused PPO pipeline with every GEMM on the 5th-gen tensor cores.
 //
 // Replaces PPOAgent.Train(Batch)'s per-sample Matrix pipeline (PPOAgent.cs:218-346; DenseLayer.FeedForward/FeedBack,
-// DenseLayer.cs:82-120) for the default networks.  Per 64-sample tile (thread = sample for the 64 "sample threads",
-// lanes 0..15 of each warp = the TMEM lanes an M=64 accumulator occupies):
+// DenseLayer.cs:82-120) for the default networks.  Per 64-sample tile (an M = 64 accumulator keeps 16 rows in each TMEM
+// sub-partition; 16x32bx2 loads let BOTH halves of a warp read columns of those rows, so every epilogue lane owns a sample and
+// a column range):
 //   F1   [64 x 16] x [16 x 128]   X|1  ->  A1pre | C1pre   (biases ride in the ones column)          tcgen05, K-major
 //   F2   [64 x 64] x [64 x 64]    A1   ->  A2pre                                                    tcgen05, K-major
-//        L3 (64->4, tanh), critic head (64->1), clipped-surrogate gradient: registers, reference summation order
+//        L3 (64->4, tanh), critic head (64->1), clipped-surrogate gradient, G2: registers, reference summation order
+//   one batch of three independent chains, one issuer warp each:
 //   dW3' [128 x 64s] x [64s x 8]  [C1|A2]^T x [g3|gv]      -> dWc2, dW3 (accumulated in TMEM over all tiles)  MN-major
 //   B2   [64 x 64] x [64 x 64]    G2 x W2 -> dL/dA1                                                 K-major A, MN-major B
-//   dW2  [64 x 64s] x [64s x 64]  G2^T x A1                (accumulated)                             MN-major
-//   dB2  [64 x 64s] x [64s x 16]  G2^T x [X|1]             (column 12 = db2, accumulated)            MN-major
+//   dW2' [64 x 64s] x [64s x 96]  G2^T x [X | 1 | .. | A1] -> db2 (column 12), dW2 (columns 32..95), accumulated      MN-major
 //   dW1  [128 x 64s] x [64s x 16] [G1|Gc1]^T x [X|1]       -> dW1, db1, dWc1, dbc1 (accumulated)     MN-major
+// Every MMA's descriptors are compile-time offsets from the chain's base descriptors (issue_chain_ct).  With one process the
+// kernel also reduces its per-CTA partials behind a grid barrier and applies Adam (FusedTail): Train(Batch) in ONE launch.
 // All operand tiles use the dual-use B32 layout above, fp32 accuracy via 3xTF32 (hi*hi + lo*hi + hi*lo).
 // ============================================================================================================
 constexpr int kS = 64;           // samples per tile
 constexpr int kBlk = kS * 32;    // floats in one 32-feature block of a 64-row tile (8 KB)
 // warps 0..7: epilogue / per-sample math -- warp w works on TMEM sub-partition w % 4 (the 16 rows an M=64 accumulator keeps
 // there) and on HALF w / 4 of the columns of every phase (half 0: A1, G1 and columns 0..31 of A2/G2; half 1: C1, value, gv,
-// Gc1 and columns 32..63 of A2/G2), so the per-sample element-wise work of a tile is spread over 128 threads; warp 8: MMA issuer
-constexpr int kTcThreads = 288;
+// Gc1 and columns 32..63 of A2/G2); inside a warp lanes 0..15 and 16..31 split that half's columns again, so the per-sample
+// element-wise work of a tile is spread over all 256 threads; warps 8..10: MMA issuers (lane 0 each)
+constexpr int kTcThreads = 352;  // 8 epilogue warps + 3 issuer warps (one elected lane each)
 
 struct __align__(1024) TcSmem {
   // nine 32-feature blocks per part, contiguous so that neighbouring blocks can be read as ONE wider operand:
@@ -288,7 +292,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   const bool is_sample = epi && lane < 16;         // lanes 32w..32w+15 hold rows 16w..16w+15 of an M=64 accumulator
   const int s_loc = (warp & 3) * 16 + (lane & 15);
   const int lh = lane >> 4;                        // which half of the warp's column range this lane owns (16x32bx2 loads)
-  const bool issuer = tid == 256;                  // lane 0 of the dedicated issuer warp: tcgen05.mma / commit
+  // lane 0 of warps 8..10: three MMA issuers.  A tcgen05.mma costs its issuing thread ~50 cycles of descriptor arithmetic and
+  // elect / retry bookkeeping however small the product is, so independent chains are issued from different warps; every issuer
+  // commits its own MMAs to the phase's mbarrier (3 arrivals per phase)
+  const bool issuer = warp >= 8 && lane == 0;
+  const int iid = warp - 8;
   const bool grad = p.mode == kModeGrad;
 
 #ifdef WB_TC_PROFILE
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 #endif
   if (warp == 0) tc::tmem_alloc(&S.tmem_slot, kTmemCols);
   if (tid == 0) {
-    tc::mbar_init(&S.mbar, 1);
+    tc::mbar_init(&S.mbar, 3);
     tc::mbar_fence_init();
   }
   // ---- weights -> dual-use tiles (once per CTA).  The activation tiles and the W1 tile are cleared first (16-byte stores): every
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(0);  // P0: stage X + sync
     // ---- P1: F1 = [X|1] x [W1|b1 ; Wc1|bc1]^T  -> 128 columns
     if (issuer) {
-      issue_chain_ct<64, 128, kKMajor, kS, kKMajor, 128, 2>(tmem + kColF1, sm_xt_hi, sm_xt_lo, sm_w1_hi, sm_w1_lo, false);
+      if (iid == 0) issue_chain_ct<64, 128, kKMajor, kS, kKMajor, 128, 2>(tmem + kColF1, sm_xt_hi, sm_xt_lo, sm_w1_hi, sm_w1_lo, false);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(2);  // P2: A1 / C1 epilogue + sync
     // ---- P3: F2 = A1 x W2^T
     if (issuer) {
-      issue_chain_ct<64, 64, kKMajor, kS, kKMajor, kHid, 8>(tmem + kColF2, sm_act_hi, sm_act_lo, sm_w2_hi, sm_w2_lo, false);
+      if (iid == 0) issue_chain_ct<64, 64, kKMajor, kS, kKMajor, kHid, 8>(tmem + kColF2, sm_act_hi, sm_act_lo, sm_w2_hi, sm_w2_lo, false);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -650,10 +658,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(7);  // G2 epilogue + sync
     // ---- P5/P6 in one batch: [C1|A2]^T x [g3|gv] (dWc2, dW3) ; dL/dA1 = G2 x W2 ; G2^T x [X | 1 | .. | A1] (db2, dW2)
     if (issuer) {
-      issue_chain_ct<128, 8, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW3, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes,
-                                                            sm_xt_hi + kG3vFeature * 4, sm_xt_lo + kG3vFeature * 4, any_tile);
-      issue_chain_ct<64, 64, kKMajor, kS, kMnMajor, kHid, 8>(tmem + kColB2, sm_g2_hi, sm_g2_lo, sm_w2_hi, sm_w2_lo, false);
-      issue_chain_ct<64, 96, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW2, sm_g2_hi, sm_g2_lo, sm_xt_hi, sm_xt_lo, any_tile);
+      if (iid == 2)
+        issue_chain_ct<128, 8, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW3, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes,
+                                                              sm_xt_hi + kG3vFeature * 4, sm_xt_lo + kG3vFeature * 4, any_tile);
+      if (iid == 0) issue_chain_ct<64, 64, kKMajor, kS, kMnMajor, kHid, 8>(tmem + kColB2, sm_g2_hi, sm_g2_lo, sm_w2_hi, sm_w2_lo, false);
+      if (iid == 1) issue_chain_ct<64, 96, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW2, sm_g2_hi, sm_g2_lo, sm_xt_hi, sm_xt_lo, any_tile);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -688,10 +697,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     TC_MARK(9);  // P7: G1 / Gc1 epilogue + sync
     // ---- P8: [G1|Gc1]^T x [X|1]  (accumulates dW1, db1, dWc1, dbc1)
     if (issuer) {
-      issue_chain_ct<128, 16, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW1, sm_act_hi, sm_act_lo, sm_xt_hi, sm_xt_lo, any_tile);
+      if (iid == 0) issue_chain_ct<128, 16, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW1, sm_act_hi, sm_act_lo, sm_xt_hi, sm_xt_lo, any_tile);
       tc::mma_commit(&S.mbar);
     }
-    if (epi) tc::mbar_wait(&S.mbar, phase);  // the next tile overwrites XT and ACT
+    tc::mbar_wait(&S.mbar, phase);  // EVERY warp (the issuer warps stage X too): the next tile overwrites the X block and the tiles dW1 reads
     phase ^= 1;
     __syncwarp();
     tc::fence_after_thread_sync();
