@@ -726,9 +726,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
         float v[16];
         tc::tmem_ld_x16(tmem_warp + kColDW2 + 32 + c, v);
         tc::tmem_ld_wait();
-        if (is_sample)
+        if (is_sample) {  // 16 consecutive floats of row o: four 16-byte stores
+          float4* dst = reinterpret_cast<float4*>(out + kOffW2 + s_loc * kHid + c);
 #pragma unroll
-          for (int j = 0; j < 16; j++) out[kOffW2 + s_loc * kHid + c + j] = v[j];
+          for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
       }
       {
         float v[16];
@@ -743,8 +745,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
         tc::tmem_ld_wait();
         const int o = tid & 63;
         const int offW = tid < 64 ? kOffW1 : kOffWc1, offB = tid < 64 ? kOffB1 : kOffBc1;
+        float4* dst = reinterpret_cast<float4*>(out + offW + o * kIn);  // 12 consecutive floats, 48-byte rows: 16-byte aligned
 #pragma unroll
-        for (int j = 0; j < kIn; j++) out[offW + o * kIn + j] = v[j];
+        for (int j = 0; j < 3; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         out[offB + o] = v[12];
       }
       // rows 0..63 = C1 features -> dWc2 (column 4); rows 64..127 = A2 features -> dW3[k][feature] (columns 0..3)
@@ -799,15 +802,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     const int per = (kGradFloats + (int)gridDim.x - 1) / (int)gridDim.x;
     const int lo = (int)blockIdx.x * per;
     const int hi = min(lo + per, kGradFloats);
-    constexpr int kLanesPer = 8;  // threads per element: each sums every 8th partial, then a butterfly (fixed order: deterministic)
+    constexpr int kLanesPer = 8;   // threads per element: each sums every 8th partial, then a butterfly (fixed order: deterministic)
+    constexpr int kMaxLoads = 20;  // partials per thread kept in flight at once (8 x 20 = 160 >= the CTAs of a 148-SM grid)
     const int part = tid & (kLanesPer - 1);
     for (int base = lo; base < hi; base += kTcThreads / kLanesPer) {  // (uniform trip count: the shuffles below are unconditional)
       const int e = base + (tid / kLanesPer);
       const bool in = e < hi;
       float acc = 0.f;
-      if (in) {
-#pragma unroll 4
-        for (int q = part; q < (int)gridDim.x; q += kLanesPer) acc += __ldcg(p.partials + (size_t)q * kGradFloats + e);
+      for (int q0 = 0; q0 < (int)gridDim.x; q0 += kLanesPer * kMaxLoads) {
+        float v[kMaxLoads];
+#pragma unroll
+        for (int j = 0; j < kMaxLoads; j++) {  // all loads of the chunk are issued before the first add
+          const int q = q0 + part + j * kLanesPer;
+          v[j] = (in && q < (int)gridDim.x) ? __ldcg(p.partials + (size_t)q * kGradFloats + e) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxLoads; j++) acc += v[j];
       }
 #pragma unroll
       for (int m = 1; m < kLanesPer; m <<= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, m);
