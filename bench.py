@@ -24,13 +24,13 @@ Keys beside the base contract (every one of them measured in this run, on this b
   cpu_baseline   the oracle port of the same physics workload on the box's host threads, rank 0, at EVERY N (bounded sample)
   at_scale       the same step on 262 144 walkers per GPU (throughput regime) + iterations_1 (one substep per launch: the record
                  really crosses HBM every substep)
-  secondary      BASELINE configs[2]: PPO samples/s on one 65 536-sample minibatch (gradient kernel + fused reduce/Adam), with
-                 its own e2e (host buffers through wb_ppo_grad + wb_adam_step), roofline (tensor) and cpu_baseline (the oracle's
+  secondary      BASELINE configs[2]: PPO samples/s on one 65 536-sample minibatch (ONE launch: gradient + reduction + Adam), with
+                 its own e2e (pinned host minibatch through PPOAgent.TrainBatch -> wb_ppo_train), roofline (tensor) and cpu_baseline (the oracle's
                  per-sample PPOAgent.Train(Batch) restatement, one thread like the reference)
   cfg1           BASELINE configs[0]: ONE walker -- the oracle port on one host thread (env-steps/s with a policy forward + sample
                  per step, and the per-sample PPO update) beside the same single-walker loop through this library
   ppo_loop       BASELINE configs[3]: the full PPO loop (rollout + returns + minibatch updates) on 65 536 walkers sharded over the
-                 N ranks; at N > 1 once with the fused reduce + all-reduce + Adam kernel over NVLink peer memory and once with the
+                 N ranks; at N > 1 once with the gradient kernel's fused reduce + all-reduce + Adam tail over NVLink peer memory and once with the
                  NCCL all-reduce: env-steps/s, samples/s, microseconds per minibatch update, spread of the weight checksums
   contact_stress BASELINE configs[4]: 16 384 walkers over the 8 floor materials, spin start, device-resident env-steps/s
 """
@@ -484,7 +484,7 @@ def bench_ppo(cx, steps, warmup):
     l0 = agent.launch_count()
     ms = cx.timed_steps(one, steps) / steps
     launches = agent.launch_count() - l0
-    # end to end through the host-buffer API: pinned host minibatch in (wb_ppo_grad copies it), losses out, then wb_adam_step
+    # end to end through the host-buffer API: pinned host minibatch in (the kernel reads it in place over PCIe), losses out
     pinned = [torch.from_numpy(x).pin_memory().numpy() for x in batch]
     for _ in range(2):
         agent.TrainBatch(*pinned)
@@ -493,7 +493,7 @@ def bench_ppo(cx, steps, warmup):
         cx.flush()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        agent.TrainBatch(*pinned)   # wb_ppo_grad (5 H2D copies, kernels, D2H of the losses, sync) + wb_adam_step
+        agent.TrainBatch(*pinned)   # wb_ppo_train: one launch reading the pinned minibatch in place, D2H of the losses, sync
         agent.sync()
         e2e_ms += (time.perf_counter() - t0) * 1e3
     e2e_ms /= steps
@@ -505,7 +505,8 @@ def bench_ppo(cx, steps, warmup):
            "config": {"workload": "65536-sample minibatch, synthetic obs (BASELINE.json configs[2])"},
            "gpu_launches": launches,
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * 22 * 4,
-                   "d2h_bytes_per_step": 12, "path": "PPOAgent.TrainBatch -> wb_ppo_grad (pinned host minibatch) + wb_adam_step"},
+                   "d2h_bytes_per_step": 12, "path": "PPOAgent.TrainBatch -> wb_ppo_train: ONE launch (gradient + reduction + Adam) that reads the pinned host "
+                                                      "minibatch in place over PCIe (zero-copy), then a 12-byte D2H of the losses + sync"},
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops,
                         "traffic": traffic, "traffic_source": traffic_src,
                         "note": f"32640 flop/sample; peak = {which} dense bf16 (the kernel computes in fp32 accuracy: 3xTF32 on tcgen05)"}}
@@ -537,8 +538,8 @@ def bench_cfg1_gpu(cx, env_steps=300):
 
 def bench_ppo_loop(cx, fused):
     """configs[3]: 65 536 walkers sharded over the ranks, horizon 64, global minibatch 65 536, one epoch: rollout (2 launches per
-    env-step) + bootstrap value + returns + 64 minibatch updates, each with ONE gradient exchange (fused kernel over NVLink peer
-    memory, or NCCL all-reduce)."""
+    env-step) + bootstrap value + returns + 64 minibatch updates, each ONE launch that reads its permuted rows of the pool,
+    reduces, exchanges the gradient over NVLink peer memory and applies Adam (or: gather + gradient kernel + NCCL all-reduce + Adam)."""
     torch = cx.torch
     vp = cx.wb.VectorPPO(N_ENVS_LOOP, horizon=64, minibatch_global=65536, epochs=1, floor="Wood", seed=11, fused_allreduce=fused)
     vp.iterate()  # warm-up (also takes the walkers off the identical start state)
@@ -559,8 +560,10 @@ def bench_ppo_loop(cx, fused):
     if cx.world > 1:
         cx.dist.all_reduce(lo, op=cx.dist.ReduceOp.MIN)
         cx.dist.all_reduce(hi, op=cx.dist.ReduceOp.MAX)
-    out = {"exchange": ("fused reduce + all-reduce + Adam kernel over NVLink peer memory" if (vp.fused and cx.world > 1) else
-                        "NCCL all-reduce + Adam kernel" if cx.world > 1 else "single rank: fused reduce + Adam kernel, nothing exchanged"),
+    out = {"exchange": ("one launch per minibatch: gradient kernel with fused reduce + all-reduce (NVLink peer memory) + Adam tail"
+                        if (vp.fused and cx.world > 1) else
+                        "gather + gradient kernel + NCCL all-reduce + Adam kernel" if cx.world > 1 else
+                        "single rank: one launch per minibatch (gradient + reduction + Adam), nothing exchanged"),
            "loop_env_steps_per_s": env_steps / ((roll + upd) * 1e-3), "rollout_env_steps_per_s": env_steps / (roll * 1e-3),
            "update_samples_per_s": n_mb * 65536 / (upd * 1e-3), "us_per_minibatch_update": upd / n_mb * 1e3,
            "minibatches": n_mb, "iterations": its, "weights_checksum_spread": float((hi - lo).item())}

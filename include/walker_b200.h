@@ -286,11 +286,22 @@ int32_t wb_comm_connect(wb_policy* p, int32_t rank, int32_t world, const void* a
 int32_t wb_comm_status(wb_policy* p, int32_t* connected_world_out, int32_t* failed_out);
 int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
                                   const float* advantages_dev, const float* returns_dev);
-/* PPOAgent.Train(Batch) complete (PPOAgent.cs:218-345) in TWO launches: the gradient kernel, then ONE kernel that reduces the per-CTA
- * partials, all-reduces them over NVLink when the policy is connected (wb_comm_connect; a single rank otherwise) and applies
- * DenseLayer.Adam to both networks -- the reduced gradient is also left in the gradient buffer (losses / skipped included) */
+/* PPOAgent.Train(Batch) complete (PPOAgent.cs:218-345): gradient, reduction of the per-CTA partials, all-reduce over NVLink when
+ * the policy is connected (wb_comm_connect; a single rank otherwise) and DenseLayer.Adam on both networks; the reduced gradient is
+ * also left in the gradient buffer (losses / skipped included).  With the default networks and the tensor-core kernel this is ONE
+ * launch: the gradient kernel reduces, exchanges and applies Adam in its own tail behind a grid barrier (every rank must then pass
+ * the same n, so that the ranks' slices agree); otherwise the gradient kernel is followed by one reduce / exchange / Adam kernel. */
 int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
                          const float* advantages_dev, const float* returns_dev);
+/* The same on rows index_dev[0..n) of a rollout pool: PPOAgent.CreateBatches (PPOAgent.cs:501-540) fused into the gradient kernel's
+ * input prefetch (no gathered copy of the minibatch is written; kernels without that path gather first, as wb_gather_minibatch_dev) */
+int32_t wb_ppo_train_indexed_dev(wb_policy* p, int32_t n, const int32_t* index_dev, const float* states_pool, const float* actions_pool,
+                                 const float* logp_pool, const float* advantages_pool, const float* returns_pool);
+/* PPOAgent.Train(Batch) from host buffers: wb_ppo_grad + wb_adam_step as one call (one launch on the default path).  When all five
+ * buffers are page-locked (cudaHostAlloc / cudaHostRegister / wb_host_pin) and 16-byte aligned the kernel reads them in place over
+ * PCIe while it computes (no staging copy); wb_ppo_grad takes the same zero-copy path.  losses / skipped as wb_ppo_grad. */
+int32_t wb_ppo_train(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
+                     const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host);
 /* NeuralNetwork.Optimise -> DenseLayer.Adam on both networks (NeuralNetwork.cs:85-91, DenseLayer.cs:125-159) */
 int32_t wb_adam_step(wb_policy* p);
 /* device address + length of the contiguous gradient buffer [actor | critic | 2 loss sums | skipped] for the

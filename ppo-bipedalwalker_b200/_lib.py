@@ -124,6 +124,8 @@ def lib() -> C.CDLL:
         "wb_comm_status": (C.c_int32, [vp, ip, ip]),
         "wb_ppo_grad_allreduce_dev": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp]),
         "wb_ppo_train_dev": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp]),
+        "wb_ppo_train_indexed_dev": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp, vp]),
+        "wb_ppo_train": (C.c_int32, [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
         "wb_segment_returns_dev": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]),
         "wb_normalize_advantages_dev": (C.c_int32, [vp, C.c_int32, C.c_int64, C.c_int64, vp]),
         "wb_normalize_stats_buffer": (C.c_int32, [vp, C.POINTER(vp), ip]),

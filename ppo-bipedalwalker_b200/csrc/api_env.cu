@@ -543,24 +543,6 @@ int32_t wb_env_get_obs(wb_env_batch* env, float* obs_host) {
   return copy_out(env, obs_host, nullptr, nullptr);
 }
 
-// Pinned (page-locked) host memory is addressable from the device under unified addressing: the device-side alias of `p`, or
-// null when `p` is ordinary pageable memory
-static void* device_alias_of_pinned(const void* p, size_t bytes) {
-  cudaPointerAttributes a{}, b{};
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeHost || !a.devicePointer) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  // the last byte must be page-locked too and alias at the same distance (one contiguous mapping, or pages pinned by wb_host_pin)
-  const char* last = static_cast<const char*>(p) + bytes - 1;
-  if (cudaPointerGetAttributes(&b, last) != cudaSuccess || b.type != cudaMemoryTypeHost ||
-      static_cast<char*>(b.devicePointer) - static_cast<char*>(a.devicePointer) != (ptrdiff_t)(bytes - 1)) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  return a.devicePointer;
-}
-
 static int step_phases(int32_t auto_reset) {
   return kPhaseIncSteps | kPhaseTakeActions | kPhaseStepObjects | kPhaseObserve | (auto_reset ? kPhaseAutoReset : 0);
 }
@@ -575,10 +557,10 @@ int32_t wb_env_step(wb_env_batch* env, const float* actions_host, float delta_ti
   static const bool zero_copy_enabled = getenv("WB_NO_ZERO_COPY") == nullptr;
   if (zero_copy_enabled) {
     const size_t n = (size_t)env->n;
-    const float* a = static_cast<const float*>(device_alias_of_pinned(actions_host, sizeof(float) * WB_ACT * n));
-    float* o = obs_host ? static_cast<float*>(device_alias_of_pinned(obs_host, sizeof(float) * WB_OBS * n)) : env->d_obs;
-    float* r = reward_host ? static_cast<float*>(device_alias_of_pinned(reward_host, sizeof(float) * n)) : env->d_reward;
-    uint8_t* d = done_host ? static_cast<uint8_t*>(device_alias_of_pinned(done_host, n)) : env->d_done;
+    const float* a = static_cast<const float*>(wb::device_alias_of_pinned(actions_host, sizeof(float) * WB_ACT * n));
+    float* o = obs_host ? static_cast<float*>(wb::device_alias_of_pinned(obs_host, sizeof(float) * WB_OBS * n)) : env->d_obs;
+    float* r = reward_host ? static_cast<float*>(wb::device_alias_of_pinned(reward_host, sizeof(float) * n)) : env->d_reward;
+    uint8_t* d = done_host ? static_cast<uint8_t*>(wb::device_alias_of_pinned(done_host, n)) : env->d_done;
     if (a && o && r && d && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
       if (int32_t rc = launch(env, step_phases(auto_reset), delta_time, a, o, r, d, nullptr, nullptr, nullptr)) return rc;
       WB_CUDA(cudaStreamSynchronize(env->stream));

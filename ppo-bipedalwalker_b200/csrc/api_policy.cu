@@ -1,5 +1,6 @@
 // api_policy.cu -- C ABI for the PPO policy/value networks (include/walker_b200.h).  Compute is in mlp.cu.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -622,21 +623,44 @@ static cudaError_t adam_any(wb_policy* p) {
   return launch_adam_generic(g, p->stream);
 }
 
-int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
-                         const float* advantages_dev, const float* returns_dev) {
-  WB_REQUIRE(p && states_dev && actions_dev && old_logp_dev && advantages_dev && returns_dev, "null argument");
+// the five device inputs of a gradient call + an optional row index (PPOAgent.CreateBatches fused into the kernel's prefetch)
+struct TrainInputs {
+  const float *states, *actions, *old_logp, *advantages, *returns;
+  const int32_t* index;
+};
+
+static int32_t train_on_device(wb_policy* p, int32_t n, TrainInputs in) {
   WB_REQUIRE(n > 0, "n must be positive");
   WB_REQUIRE(p->hp.batch_size > 0, "batch_size must be positive");
   if (int32_t rc = comm_healthy(p)) return rc;
+  const int world = p->comm_world >= 2 ? p->comm_world : 1;
+  const int grid = grid_of(p, n);
+  const bool one_launch = !use_generic(p) && p->variant == 0 && grid <= p->sm_count;
+  if (in.index && !one_launch) {
+    // the other kernels read contiguous minibatches: gather the rows first (PPOAgent.CreateBatches as its own launch)
+    if (p->actor.input != kIn || p->actor.output != kAct)
+      return fail(WB_ERR_UNSUPPORTED, "the minibatch gather is laid out for 12 observations and 4 actions");
+    const size_t N = (size_t)n;
+    if (int32_t rc = ensure_stage(p, N * (kIn + kAct + kAct + 2))) return rc;
+    float* g_states = p->d_stage;
+    float* g_actions = g_states + N * kIn;
+    float* g_logp = g_actions + N * kAct;
+    float* g_adv = g_logp + N * kAct;
+    float* g_ret = g_adv + N;
+    WB_CUDA(launch_gather_minibatch(in.index, n, in.states, in.actions, in.old_logp, in.advantages, in.returns, g_states, g_actions, g_logp,
+                                    g_adv, g_ret, p->stream));
+    p->launches++;
+    in = TrainInputs{g_states, g_actions, g_logp, g_adv, g_ret, nullptr};
+  }
   MlpParams m;
   fill_mlp_common(p, m, n, kModeGrad);
-  m.states = states_dev;
-  m.actions = actions_dev;
-  m.old_logp = old_logp_dev;
-  m.advantages = advantages_dev;
-  m.returns = returns_dev;
+  m.states = in.states;
+  m.actions = in.actions;
+  m.old_logp = in.old_logp;
+  m.advantages = in.advantages;
+  m.returns = in.returns;
+  m.index = in.index;
   m.partials = p->d_partials;
-  const int grid = grid_of(p, n);
   if (use_generic(p)) {  // any topology: reduction and Adam as separate launches (single rank; data-parallel callers use the NCCL path)
     WB_REQUIRE(p->comm_world < 2, "a connected policy needs the default networks and kernel variant 0 or 1");
     WB_CUDA(run_mlp(p, m));
@@ -647,10 +671,9 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
   }
   AdamParams a;
   next_adam_params(p, a);
-  const int world = p->comm_world >= 2 ? p->comm_world : 1;
-  if (world == 1 && p->variant == 0 && grid <= p->sm_count) {
-    // ONE launch: the tensor-core gradient kernel reduces its own partials behind a grid barrier and applies Adam (the grid is
-    // persistent, one CTA per SM, so every CTA is resident)
+  if (one_launch) {
+    // ONE launch: the tensor-core gradient kernel reduces its own partials behind a grid barrier (the grid is persistent, one CTA
+    // per SM, so every CTA is resident), exchanges its slices with the peers over NVLink when connected, and applies Adam
     FusedTail t{};
     t.enabled = 1;
     t.counter = p->d_grid_sync;
@@ -658,6 +681,13 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
     t.target = p->grid_sync_target;
     t.grads = p->d_grads;
     t.adam = a;
+    t.world = world;
+    if (world > 1) {
+      t.peers = p->peers;
+      t.rank = p->comm_rank;
+      t.epoch = ++p->comm_epoch;
+      t.status = p->d_comm_status;
+    }
     WB_CUDA(launch_mlp_tc(m, grid, p->stream, &t));
     p->launches += 1;
     return WB_OK;
@@ -670,12 +700,38 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
   return WB_OK;
 }
 
-int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
-                    const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host) {
-  WB_REQUIRE(p && states_host && actions_host && old_logp_host && advantages_host && returns_host, "null argument");
-  WB_REQUIRE(n > 0, "n must be positive");
+int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
+                         const float* advantages_dev, const float* returns_dev) {
+  WB_REQUIRE(p && states_dev && actions_dev && old_logp_dev && advantages_dev && returns_dev, "null argument");
+  return train_on_device(p, n, TrainInputs{states_dev, actions_dev, old_logp_dev, advantages_dev, returns_dev, nullptr});
+}
+
+int32_t wb_ppo_train_indexed_dev(wb_policy* p, int32_t n, const int32_t* index_dev, const float* states_pool, const float* actions_pool,
+                                 const float* logp_pool, const float* advantages_pool, const float* returns_pool) {
+  WB_REQUIRE(p && index_dev && states_pool && actions_pool && logp_pool && advantages_pool && returns_pool, "null argument");
+  return train_on_device(p, n, TrainInputs{states_pool, actions_pool, logp_pool, advantages_pool, returns_pool, index_dev});
+}
+
+// device view of a host minibatch: the buffers' own device aliases when all five are page-locked (the kernel then reads them over
+// PCIe while it computes: no staging copy), else a staged copy
+static int32_t minibatch_on_device(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
+                                   const float* advantages_host, const float* returns_host, TrainInputs* out) {
   const size_t IN = (size_t)p->actor.input, ACT = (size_t)p->actor.output;
   const size_t N = (size_t)n;
+  static const bool zero_copy_enabled = getenv("WB_NO_ZERO_COPY") == nullptr;
+  if (zero_copy_enabled) {
+    const float* s = static_cast<const float*>(device_alias_of_pinned(states_host, sizeof(float) * N * IN));
+    const float* a = static_cast<const float*>(device_alias_of_pinned(actions_host, sizeof(float) * N * ACT));
+    const float* l = static_cast<const float*>(device_alias_of_pinned(old_logp_host, sizeof(float) * N * ACT));
+    const float* ad = static_cast<const float*>(device_alias_of_pinned(advantages_host, sizeof(float) * N));
+    const float* r = static_cast<const float*>(device_alias_of_pinned(returns_host, sizeof(float) * N));
+    const uintptr_t all = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(l) |
+                          reinterpret_cast<uintptr_t>(ad) | reinterpret_cast<uintptr_t>(r);
+    if (s && a && l && ad && r && (all & 15) == 0) {  // (the kernels use vector loads)
+      *out = TrainInputs{s, a, l, ad, r, nullptr};
+      return WB_OK;
+    }
+  }
   if (int32_t rc = ensure_stage(p, N * (IN + ACT + ACT + 2))) return rc;
   float* d_states = p->d_stage;
   float* d_actions = d_states + N * IN;
@@ -687,7 +743,11 @@ int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const flo
   WB_CUDA(cudaMemcpyAsync(d_logp, old_logp_host, sizeof(float) * N * ACT, cudaMemcpyHostToDevice, p->stream));
   WB_CUDA(cudaMemcpyAsync(d_adv, advantages_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
   WB_CUDA(cudaMemcpyAsync(d_ret, returns_host, sizeof(float) * N, cudaMemcpyHostToDevice, p->stream));
-  if (int32_t rc = wb_ppo_grad_dev(p, n, d_states, d_actions, d_logp, d_adv, d_ret)) return rc;
+  *out = TrainInputs{d_states, d_actions, d_logp, d_adv, d_ret, nullptr};
+  return WB_OK;
+}
+
+static int32_t read_losses(wb_policy* p, float* losses_host, int32_t* skipped_host) {
   float tail[3] = {0.f, 0.f, 0.f};
   WB_CUDA(cudaMemcpyAsync(tail, p->d_grads + p->n_total, sizeof(tail), cudaMemcpyDeviceToHost, p->stream));
   WB_CUDA(cudaStreamSynchronize(p->stream));
@@ -697,6 +757,26 @@ int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const flo
   }
   if (skipped_host) *skipped_host = (int32_t)tail[2];
   return WB_OK;
+}
+
+int32_t wb_ppo_grad(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
+                    const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host) {
+  WB_REQUIRE(p && states_host && actions_host && old_logp_host && advantages_host && returns_host, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  TrainInputs in{};
+  if (int32_t rc = minibatch_on_device(p, n, states_host, actions_host, old_logp_host, advantages_host, returns_host, &in)) return rc;
+  if (int32_t rc = wb_ppo_grad_dev(p, n, in.states, in.actions, in.old_logp, in.advantages, in.returns)) return rc;
+  return read_losses(p, losses_host, skipped_host);
+}
+
+int32_t wb_ppo_train(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
+                     const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host) {
+  WB_REQUIRE(p && states_host && actions_host && old_logp_host && advantages_host && returns_host, "null argument");
+  WB_REQUIRE(n > 0, "n must be positive");
+  TrainInputs in{};
+  if (int32_t rc = minibatch_on_device(p, n, states_host, actions_host, old_logp_host, advantages_host, returns_host, &in)) return rc;
+  if (int32_t rc = train_on_device(p, n, in)) return rc;
+  return read_losses(p, losses_host, skipped_host);
 }
 
 int32_t wb_adam_step(wb_policy* p) {

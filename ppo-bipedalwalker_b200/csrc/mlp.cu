@@ -623,12 +623,7 @@ cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream) {
 // adds the world's slots in rank order -- every rank performs the same additions in the same order, so the reduced gradient
 // (and therefore Adam and the weights) is bit-identical everywhere.  Slices are independent (no grid-wide barrier) and the
 // slots are double buffered by epoch parity: a rank can run at most one exchange ahead of the slowest peer.
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
+// (st_release_sys / ld_acquire_sys: mlp.cuh)
 
 __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ grads,
                                                                        ExchPeers peers, int rank, int world, uint32_t epoch, uint32_t* status,

@@ -47,6 +47,9 @@ struct MlpParams {
   const float* advantages; // [n]      (grad)
   const float* returns;    // [n]      (grad)
   const float* uniforms;   // [n][4][2] (sample)
+  // (grad, tensor-core kernel only) sample s of the call is row index[s] of the five input arrays -- PPOAgent.CreateBatches fused
+  // into the gradient kernel's input prefetch; nullptr = row s
+  const int32_t* index;
   uint64_t seed, step;     // (sample, philox)
   // outputs
   float* mean;         // [n][4] or null
@@ -83,17 +86,6 @@ __device__ __forceinline__ void adam_update(const AdamParams& a, int i, float g)
 }
 #endif
 
-// Tail of the gradient kernel when ONE process trains (no exchange): after a grid-wide barrier (every CTA of the persistent grid is
-// resident: one per SM) each CTA reduces its slice of the per-CTA partials in a fixed order and applies DenseLayer.Adam to it --
-// PPOAgent.Train(Batch) in ONE launch instead of gradient kernel + reduction kernel.
-struct FusedTail {
-  int32_t enabled;
-  uint32_t* counter;   // monotonically increasing arrival counter of the grid barrier
-  uint32_t target;     // value the counter reaches when every CTA of THIS launch has arrived
-  float* grads;        // [kGradFloats] reduced gradient (+ loss sums, skipped)
-  AdamParams adam;
-};
-
 int mlp_grid_for(int n, int sm_count);
 cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_reduce_partials(const float* partials, int nparts, float* grads, cudaStream_t stream);
@@ -106,16 +98,46 @@ constexpr int kExchMaxWorld = 8;
 constexpr int kExchThreads = 256;
 constexpr int kExchLanes = 16;   // threads per float4 of the gradient buffer: each sums every 16th per-CTA partial
 constexpr int kExchCtas = (kGradFloats / 4 + kExchThreads / kExchLanes - 1) / (kExchThreads / kExchLanes);  // 97 slices of 16 float4
+// flags per (parity, rank): one per CTA of whichever kernel runs the exchange -- reduce_exchange_kernel (97 CTAs) or the tail of the
+// tensor-core gradient kernel (one CTA per SM)
+constexpr int kExchFlagSlots = 192;
 struct ExchPeers {
   float* base[kExchMaxWorld];  // every rank's exchange buffer as seen from this process
 };
-// layout (floats): slots [2 parities][kExchMaxWorld ranks][kGradFloats], then flags (uint32) [2][kExchMaxWorld][kExchCtas]
+// layout (floats): slots [2 parities][kExchMaxWorld ranks][kGradFloats], then flags (uint32) [2][kExchMaxWorld][kExchFlagSlots]
 constexpr size_t kExchSlotFloats = (size_t)2 * kExchMaxWorld * kGradFloats;
-constexpr size_t kExchBytes = kExchSlotFloats * sizeof(float) + (size_t)2 * kExchMaxWorld * kExchCtas * sizeof(uint32_t);
+constexpr size_t kExchBytes = kExchSlotFloats * sizeof(float) + (size_t)2 * kExchMaxWorld * kExchFlagSlots * sizeof(uint32_t);
 __host__ __device__ inline size_t exch_slot_offset(int parity, int rank) { return ((size_t)parity * kExchMaxWorld + rank) * kGradFloats; }
 __host__ __device__ inline uint32_t* exch_flag(float* base, int parity, int rank, int cta) {
-  return reinterpret_cast<uint32_t*>(base + kExchSlotFloats) + ((size_t)parity * kExchMaxWorld + rank) * kExchCtas + cta;
+  return reinterpret_cast<uint32_t*>(base + kExchSlotFloats) + ((size_t)parity * kExchMaxWorld + rank) * kExchFlagSlots + cta;
 }
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#endif
+
+// Tail of the tensor-core gradient kernel: PPOAgent.Train(Batch) in ONE launch.  After a grid-wide barrier (every CTA of the
+// persistent grid is resident: one per SM) each CTA reduces its slice of the per-CTA partials in a fixed order; with world > 1 it
+// then pushes the slice into slot [rank] of every peer's exchange buffer over NVLink, publishes / awaits the epoch flags of ITS
+// slice (the protocol of reduce_exchange_kernel, mlp.cu) and adds the world's slots in rank order; finally it applies
+// DenseLayer.Adam to the slice.  Every rank must launch the same grid (same n), so that the slices agree.
+struct FusedTail {
+  int32_t enabled;
+  uint32_t* counter;   // monotonically increasing arrival counter of the grid barrier
+  uint32_t target;     // value the counter reaches when every CTA of THIS launch has arrived
+  float* grads;        // [kGradFloats] reduced gradient (+ loss sums, skipped)
+  AdamParams adam;
+  // exchange (world > 1)
+  ExchPeers peers;
+  int32_t rank, world;
+  uint32_t epoch;
+  uint32_t* status;    // mapped host word: non-zero after a time-out (every later exchange is a no-op)
+};
+
 // adam != nullptr: DenseLayer.Adam is applied to the reduced gradient inside the same kernel
 cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
                                    uint32_t epoch, uint32_t* status, const AdamParams* adam, cudaStream_t stream);

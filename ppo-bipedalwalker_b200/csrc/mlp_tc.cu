@@ -392,11 +392,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       const int i = tid + q * kTcThreads;
       const int s = i >> 4, f = i & 15;
       float v = 0.f;
-      if (i < kS * 16 && s < nvalid) v = (f < kIn) ? p.states[(size_t)(s0 + s) * kIn + f] : (f == kIn ? 1.0f : 0.f);
+      if (i < kS * 16 && s < nvalid) {
+        const size_t row = p.index ? (size_t)p.index[s0 + s] : (size_t)(s0 + s);  // (the 16 threads of a sample read the same index word)
+        v = (f < kIn) ? p.states[row * kIn + f] : (f == kIn ? 1.0f : 0.f);
+      }
       x_next[q] = v;
     }
     if (grad && epi && s_loc < nvalid) {
-      const size_t g = (size_t)(s0 + s_loc);
+      const size_t g = p.index ? (size_t)p.index[s0 + s_loc] : (size_t)(s0 + s_loc);
       const int k0 = (lane >> 4) * 2;
       const float2 a2 = *reinterpret_cast<const float2*>(p.actions + g * kAct + k0);
       const float2 l2 = *reinterpret_cast<const float2*>(p.old_logp + g * kAct + k0);
@@ -788,7 +791,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
   if (grad && tail.enabled) {
-    // ---- grid barrier (all CTAs resident), then this CTA's slice of the reduction + Adam
+    // ---- grid barrier (all CTAs resident), then this CTA's slice of the reduction (+ exchange over NVLink) + Adam
     __threadfence();  // my partial is visible device-wide before I arrive
     __syncthreads();
     if (tid == 0) {
@@ -799,31 +802,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       } while ((int32_t)(seen - tail.target) < 0);
     }
     __syncthreads();
-    const int per = (kGradFloats + (int)gridDim.x - 1) / (int)gridDim.x;
+    // slices are whole float4s, so that the same partition serves every grid size a peer could also have chosen for this n
+    const int per = ((kGradFloats / 4 + (int)gridDim.x - 1) / (int)gridDim.x) * 4;
     const int lo = (int)blockIdx.x * per;
     const int hi = min(lo + per, kGradFloats);
+    const bool xchg = tail.world > 1;  // (kernel argument: uniform)
+    // a previous exchange of this handle timed out: the ranks' weights can no longer be assumed identical -- every later launch
+    // leaves the gradient buffer and the weights alone until the host has seen the status word
+    const bool dead = xchg && __syncthreads_or(tid == 0 && *reinterpret_cast<volatile uint32_t*>(tail.status) != 0u) != 0;
+    const int par = (int)(tail.epoch & 1u);
     constexpr int kLanesPer = 8;   // threads per element: each sums every 8th partial, then a butterfly (fixed order: deterministic)
     constexpr int kMaxLoads = 20;  // partials per thread kept in flight at once (8 x 20 = 160 >= the CTAs of a 148-SM grid)
+    static_assert(kLanesPer >= kExchMaxWorld, "lane r of an element pushes it to rank r");
     const int part = tid & (kLanesPer - 1);
-    for (int base = lo; base < hi; base += kTcThreads / kLanesPer) {  // (uniform trip count: the shuffles below are unconditional)
-      const int e = base + (tid / kLanesPer);
-      const bool in = e < hi;
-      float acc = 0.f;
-      for (int q0 = 0; q0 < (int)gridDim.x; q0 += kLanesPer * kMaxLoads) {
-        float v[kMaxLoads];
+    if (!dead && lo < hi) {
+      for (int base = lo; base < hi; base += kTcThreads / kLanesPer) {  // (uniform trip count: the shuffles below are unconditional)
+        const int e = base + (tid / kLanesPer);
+        const bool in = e < hi;
+        float acc = 0.f;
+        for (int q0 = 0; q0 < (int)gridDim.x; q0 += kLanesPer * kMaxLoads) {
+          float v[kMaxLoads];
 #pragma unroll
-        for (int j = 0; j < kMaxLoads; j++) {  // all loads of the chunk are issued before the first add
-          const int q = q0 + part + j * kLanesPer;
-          v[j] = (in && q < (int)gridDim.x) ? __ldcg(p.partials + (size_t)q * kGradFloats + e) : 0.f;
+          for (int j = 0; j < kMaxLoads; j++) {  // all loads of the chunk are issued before the first add
+            const int q = q0 + part + j * kLanesPer;
+            v[j] = (in && q < (int)gridDim.x) ? __ldcg(p.partials + (size_t)q * kGradFloats + e) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < kMaxLoads; j++) acc += v[j];
         }
 #pragma unroll
-        for (int j = 0; j < kMaxLoads; j++) acc += v[j];
+        for (int m = 1; m < kLanesPer; m <<= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, m);
+        if (!xchg) {
+          if (in && part == 0) {
+            tail.grads[e] = acc;
+            if (e < kTotalParams) adam_update(tail.adam, e, acc);
+          }
+        } else if (in && part < tail.world) {
+          // lane r of the element pushes it into slot [par][my rank] of rank r (NVLink store; r == rank is local)
+          tail.peers.base[part][exch_slot_offset(par, tail.rank) + e] = acc;
+        }
       }
-#pragma unroll
-      for (int m = 1; m < kLanesPer; m <<= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, m);
-      if (in && part == 0) {
-        tail.grads[e] = acc;
-        if (e < kTotalParams) adam_update(tail.adam, e, acc);
+      if (xchg) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid < tail.world) st_release_sys(exch_flag(tail.peers.base[tid], par, tail.rank, (int)blockIdx.x), tail.epoch);
+        bool timed_out = false;
+        if (tid < tail.world) {  // wait for rank tid's slice in MY buffer
+          const uint32_t* f = exch_flag(tail.peers.base[tail.rank], par, tid, (int)blockIdx.x);
+          long spins = 0;
+          while (ld_acquire_sys(f) != tail.epoch) {
+            if (++spins > (1L << 31)) {  // a peer never arrived (crashed?): give up loudly instead of hanging the GPU
+              *reinterpret_cast<volatile uint32_t*>(tail.status) = 1u;  // (mapped host memory: the host sees it without a copy)
+              __threadfence_system();
+              timed_out = true;
+              break;
+            }
+          }
+        }
+        // a slice whose peers did not all arrive holds stale slot data: it must neither be stored nor reach Adam
+        if (__syncthreads_or(timed_out) == 0) {
+          const float* mine = tail.peers.base[tail.rank];
+          for (int e = lo + tid; e < hi; e += kTcThreads) {
+            float s = 0.f;
+            for (int r = 0; r < tail.world; r++) s += __ldcg(mine + exch_slot_offset(par, r) + e);  // rank order on every rank: bit-identical sums
+            tail.grads[e] = s;
+            if (e < kTotalParams) adam_update(tail.adam, e, s);
+          }
+        }
       }
     }
   }

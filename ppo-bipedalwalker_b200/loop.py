@@ -12,8 +12,10 @@ values, returns, advantages, Epochs x shuffled mini-batches of Train(Batch) -- r
             case because it trains on complete episodes only; `bootstrap=False` truncates instead), optionally
             PPOAgent.Normalize over the global pool (two 2 KB all-reduces), then `epochs` x (pool / minibatch)
             mini-batches: index permutation (sampling without replacement, remainder dropped, PPOAgent.cs:501-540) ->
-            wb_gather_minibatch_dev -> wb_ppo_train_dev (gradient kernel + ONE kernel that reduces the partial gradients,
-            all-reduces the 6 152-float buffer over NVLink peer memory and applies Adam; NCCL all-reduce as the fallback).
+            wb_ppo_train_indexed_dev: ONE launch per mini-batch (the tensor-core gradient kernel reads the permuted rows of the
+            pool directly, reduces its per-CTA partials behind a grid barrier, all-reduces the 6 152-float buffer over NVLink
+            peer memory and applies Adam in its tail).  `fused_allreduce=False`: wb_gather_minibatch_dev -> wb_ppo_grad_dev ->
+            NCCL all-reduce -> wb_adam_step (the fallback and cross-check).
 
 Multi-GPU (one process per GPU, torchrun): the walkers are block-sharded, rollouts never communicate; every rank draws its
 share (minibatch / world) of each global mini-batch from its OWN pool, gradients are divided by the GLOBAL batch size inside
@@ -132,11 +134,12 @@ class VectorPPO:
             perm = torch.randperm(self.pool_local, generator=self.gen, device=S.device, dtype=torch.int32)
             for j in range(n_mb):
                 idx = perm[j * self.mb_local:(j + 1) * self.mb_local]
-                check(L.wb_gather_minibatch_dev(h, self.mb_local, ptr(idx), ptr(S), ptr(A), ptr(LP), ptr(ADV), ptr(RET), *[ptr(m) for m in self.mb]))
                 if self.fused or self.world == 1:
-                    # gradient kernel, then ONE kernel: reduce partials (+ all-reduce over NVLink peer memory) + Adam
-                    check(L.wb_ppo_train_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
+                    # ONE launch per mini-batch: the gradient kernel reads rows idx[] of the pool (CreateBatches fused into its
+                    # prefetch), reduces its partials, all-reduces them over NVLink peer memory and applies Adam in its tail
+                    check(L.wb_ppo_train_indexed_dev(h, self.mb_local, ptr(idx), ptr(S), ptr(A), ptr(LP), ptr(ADV), ptr(RET)))
                 else:
+                    check(L.wb_gather_minibatch_dev(h, self.mb_local, ptr(idx), ptr(S), ptr(A), ptr(LP), ptr(ADV), ptr(RET), *[ptr(m) for m in self.mb]))
                     check(L.wb_ppo_grad_dev(h, self.mb_local, *[ptr(m) for m in self.mb]))
                     _dist.allreduce_sum_(self.grad_view)
                     check(L.wb_adam_step(h))

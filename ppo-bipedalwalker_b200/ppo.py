@@ -268,14 +268,18 @@ class PPOAgent:
         return actions, logp, mean, std
 
     # -- training
-    def Gradients(self, states, actions, logProbabilities, advantages, returns):
-        """Gradient half of PPOAgent.Train(Batch) (PPOAgent.cs:218-342). Returns (criticLoss, actorLoss, skipped)."""
+    def _minibatch(self, states, actions, logProbabilities, advantages, returns):
         s = np.ascontiguousarray(states, np.float32).reshape(-1, self.stateSize)
         n = s.shape[0]
         a = np.ascontiguousarray(actions, np.float32).reshape(n, self.actionSize)
         lp = np.ascontiguousarray(logProbabilities, np.float32).reshape(n, self.actionSize)
         adv = np.ascontiguousarray(advantages, np.float32).reshape(n)
         ret = np.ascontiguousarray(returns, np.float32).reshape(n)
+        return n, s, a, lp, adv, ret
+
+    def Gradients(self, states, actions, logProbabilities, advantages, returns):
+        """Gradient half of PPOAgent.Train(Batch) (PPOAgent.cs:218-342). Returns (criticLoss, actorLoss, skipped)."""
+        n, s, a, lp, adv, ret = self._minibatch(states, actions, logProbabilities, advantages, returns)
         losses = np.zeros(2, np.float32)
         skipped = C.c_int32(0)
         check(lib().wb_ppo_grad(self._h, n, ptr(s), ptr(a), ptr(lp), ptr(adv), ptr(ret), ptr(losses), C.byref(skipped)))
@@ -285,10 +289,13 @@ class PPOAgent:
         check(lib().wb_adam_step(self._h))
 
     def TrainBatch(self, states, actions, logProbabilities, advantages, returns):
-        """PPOAgent.Train(Batch): zero, accumulate, Adam."""
-        out = self.Gradients(states, actions, logProbabilities, advantages, returns)
-        self.Optimise()
-        return out
+        """PPOAgent.Train(Batch) (PPOAgent.cs:218-345): zero, accumulate, Adam -- one call (wb_ppo_train: one launch on the default
+        path; page-locked input arrays are read in place). Returns (criticLoss, actorLoss, skipped)."""
+        n, s, a, lp, adv, ret = self._minibatch(states, actions, logProbabilities, advantages, returns)
+        losses = np.zeros(2, np.float32)
+        skipped = C.c_int32(0)
+        check(lib().wb_ppo_train(self._h, n, ptr(s), ptr(a), ptr(lp), ptr(adv), ptr(ret), ptr(losses), C.byref(skipped)))
+        return float(losses[0]), float(losses[1]), skipped.value
 
     def CalculateValues(self, trajectory: Trajectory):  # PPOAgent.cs:175-189
         states = np.asarray(trajectory.States, np.float32).reshape(-1, self.stateSize)

@@ -379,6 +379,64 @@ def test_single_launch_train_step_matches_gradient_then_adam(gpu, O):
         assert list(iters) == [3, 3, 3]
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_indexed_train_step_equals_gather_then_train(gpu, O, variant):
+    """wb_ppo_train_indexed_dev trains on rows index[] of a rollout pool (PPOAgent.CreateBatches, PPOAgent.cs:501-540, fused into
+    the tensor-core kernel's prefetch; the other kernels gather first): same weights, bit for bit, as wb_gather_minibatch_dev
+    followed by wb_ppo_train_dev, and the oracle's update on the gathered rows."""
+    import torch
+    from ppo_bipedalwalker_b200._lib import check, lib, ptr
+    pool_n, n = 3000, 1000
+    direct, actor, critic, ohp = make_pair(gpu, O, 41, n, variant=variant)
+    gathered, _, _, _ = make_pair(gpu, O, 41, n, variant=variant)
+    rng = np.random.default_rng(41)
+    pool = synth_batch(rng, actor, pool_n, critic_flat=critic.get_params())
+    dev_pool = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in pool]
+    mb = [torch.empty((n,) + tuple(t.shape[1:]), dtype=torch.float32, device="cuda") for t in dev_pool]
+    for step in range(3):
+        idx = rng.permutation(pool_n)[:n].astype(np.int32)
+        dev_idx = torch.from_numpy(idx).cuda()
+        check(lib().wb_ppo_train_indexed_dev(direct._h, n, ptr(dev_idx), *[ptr(t) for t in dev_pool]))
+        check(lib().wb_gather_minibatch_dev(gathered._h, n, ptr(dev_idx), *[ptr(t) for t in dev_pool], *[ptr(t) for t in mb]))
+        check(lib().wb_ppo_train_dev(gathered._h, n, *[ptr(t) for t in mb]))
+        direct.sync()
+        gathered.sync()
+        O.ppo_train_batch(actor, critic, ohp, *[x[idx] for x in pool], optimise=True)
+        for net_d, net_g, net_o in ((direct.actor, gathered.actor, actor), (direct.critic, gathered.critic, critic)):
+            np.testing.assert_array_equal(net_d.get_flat(), net_g.get_flat())
+            np.testing.assert_array_equal(net_d.get_grads(), net_g.get_grads())
+            np.testing.assert_allclose(net_d.get_flat(), net_o.get_params(), rtol=0, atol=3e-5)
+
+
+def test_host_train_step_reads_pinned_buffers_in_place(gpu, O):
+    """wb_ppo_train (PPOAgent.TrainBatch) from page-locked host arrays (read in place by the kernel), from pageable ones (staged
+    copy) and wb_ppo_grad + wb_adam_step must leave identical weights, losses and skip counts; an odd sample count exercises the
+    ragged last tile."""
+    import torch
+    n = 4321
+    agents = [make_pair(gpu, O, 51, n, variant=0) for _ in range(3)]
+    pinned_agent, actor, critic, ohp = agents[0]
+    pageable_agent, split_agent = agents[1][0], agents[2][0]
+    rng = np.random.default_rng(51)
+    for step in range(2):
+        batch = list(synth_batch(rng, actor, n, critic_flat=critic.get_params()))
+        batch[2][7, 2] = -200.0  # one skipped sample (PPOAgent.cs:286-290)
+        pinned = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy() for x in batch]
+        out_pinned = pinned_agent.TrainBatch(*pinned)
+        out_pageable = pageable_agent.TrainBatch(*batch)
+        out_split = split_agent.Gradients(*batch)
+        split_agent.Optimise()
+        assert out_pinned == out_pageable and out_pinned[2] == 1
+        assert out_split[2] == 1
+        np.testing.assert_allclose(out_pinned[:2], out_split[:2], rtol=1e-5)
+        O.ppo_train_batch(actor, critic, ohp, *batch, optimise=True)
+        for which in ("actor", "critic"):
+            a, b, c = (getattr(x, which).get_flat() for x in (pinned_agent, pageable_agent, split_agent))
+            np.testing.assert_array_equal(a, b)
+            np.testing.assert_allclose(a, c, rtol=0, atol=2e-6)
+            np.testing.assert_allclose(a, {"actor": actor, "critic": critic}[which].get_params(), rtol=0, atol=3e-5)
+
+
 def test_topologies_outside_the_kernels_fail_loudly(gpu):
     with pytest.raises(gpu.WalkerB200Error):  # wider than the 128 the kernels cover: refused, never a silent fallback
         gpu.PPOAgent(actor="Input |256| (ReLU) |4| (TanH) Output")
