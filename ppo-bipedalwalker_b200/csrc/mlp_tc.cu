@@ -277,6 +277,9 @@ __device__ unsigned long long g_tc_prof[16];
 #define TC_MARK(k)
 #endif
 
+// INDEXED: sample s of the call is row p.index[s] of the input arrays (PPOAgent.CreateBatches fused into the prefetch); the row
+// numbers are fetched TWO tiles ahead, so that the row loads of the next tile never wait for an index load
+template <bool INDEXED>
 __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p, const TcConsts gc, const FusedTail tail) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -384,6 +387,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   constexpr int kXPer = (kS * 16 + kTcThreads - 1) / kTcThreads;
   float x_next[kXPer];
   float a_next[2] = {0.f, 0.f}, lp_next[2] = {0.f, 0.f}, adv_next = 0.f, ret_next = 0.f;
+  int row_x[kXPer], row_s = 0;  // (INDEXED) pool rows of the samples whose elements this thread fetches next
+  auto prefetch_rows = [&](int tile) {  // (INDEXED) row numbers of `tile`: consumed by the prefetch() call one tile later
+    const int s0 = tile * kS;
+    const int nvalid = tile < ntiles ? min(kS, p.n - s0) : 0;
+#pragma unroll
+    for (int q = 0; q < kXPer; q++) {
+      const int i = tid + q * kTcThreads;
+      const int s = i >> 4;
+      row_x[q] = (i < kS * 16 && s < nvalid) ? p.index[s0 + s] : 0;  // (the 16 threads of a sample read the same word)
+    }
+    row_s = (grad && epi && s_loc < nvalid) ? p.index[s0 + s_loc] : 0;
+  };
   auto prefetch = [&](int tile) {
     const int s0 = tile * kS;
     const int nvalid = tile < ntiles ? min(kS, p.n - s0) : 0;
@@ -393,13 +408,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       const int s = i >> 4, f = i & 15;
       float v = 0.f;
       if (i < kS * 16 && s < nvalid) {
-        const size_t row = p.index ? (size_t)p.index[s0 + s] : (size_t)(s0 + s);  // (the 16 threads of a sample read the same index word)
+        const size_t row = INDEXED ? (size_t)row_x[q] : (size_t)(s0 + s);
         v = (f < kIn) ? p.states[row * kIn + f] : (f == kIn ? 1.0f : 0.f);
       }
       x_next[q] = v;
     }
     if (grad && epi && s_loc < nvalid) {
-      const size_t g = p.index ? (size_t)p.index[s0 + s_loc] : (size_t)(s0 + s_loc);
+      const size_t g = INDEXED ? (size_t)row_s : (size_t)(s0 + s_loc);
       const int k0 = (lane >> 4) * 2;
       const float2 a2 = *reinterpret_cast<const float2*>(p.actions + g * kAct + k0);
       const float2 l2 = *reinterpret_cast<const float2*>(p.old_logp + g * kAct + k0);
@@ -410,7 +425,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       adv_next = p.advantages[g];
       ret_next = p.returns[g];
     }
+    if (INDEXED) prefetch_rows(tile + gridDim.x);
   };
+  if (INDEXED) prefetch_rows(blockIdx.x);
   prefetch(blockIdx.x);
 #ifdef WB_TC_PROFILE
   unsigned long long tc_acc[12] = {};
@@ -904,7 +921,9 @@ cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream, con
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(ppo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+    cudaError_t e = cudaFuncSetAttribute(ppo_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ppo_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -917,7 +936,10 @@ cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream, con
   gc.variance = gc.stdv * gc.stdv;
   FusedTail t{};
   if (tail) t = *tail;
-  ppo_tc_kernel<<<grid, kTcThreads, sizeof(TcSmem), stream>>>(p, gc, t);
+  if (p.index)
+    ppo_tc_kernel<true><<<grid, kTcThreads, sizeof(TcSmem), stream>>>(p, gc, t);
+  else
+    ppo_tc_kernel<false><<<grid, kTcThreads, sizeof(TcSmem), stream>>>(p, gc, t);
   return cudaGetLastError();
 }
 
