@@ -34,6 +34,7 @@ struct wb_policy {
   float* d_exch = nullptr;       // this rank's exchange buffer (kExchBytes), exported through CUDA IPC
   uint32_t* h_comm_status = nullptr;  // mapped pinned host word: set by reduce_exchange_kernel when a peer never arrived
   uint32_t* d_comm_status = nullptr;  // its device alias
+  uint32_t* d_comm_dead = nullptr;    // device-memory copy of the status word (what the kernels check at launch)
   double* d_norm_stats = nullptr;     // [2][kNormCtas] partial sums of PPOAgent.Normalize (wb_normalize_advantages_dev)
   uint32_t* d_grid_sync = nullptr;    // arrival counter of the gradient kernel's grid barrier (fused single-process tail)
   uint32_t grid_sync_target = 0;
@@ -211,6 +212,8 @@ int32_t wb_policy_create(int32_t state_size, int32_t action_size, const int32_t*
   if (e == cudaSuccess) e = cudaMalloc(&p->d_norm_stats, sizeof(double) * 2 * kNormCtas);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_grid_sync, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(p->d_grid_sync, 0, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_comm_dead, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(p->d_comm_dead, 0, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaHostAlloc(&p->h_comm_status, sizeof(uint32_t), cudaHostAllocMapped);
   if (e == cudaSuccess) {
     *p->h_comm_status = 0;
@@ -240,6 +243,7 @@ int32_t wb_policy_destroy(wb_policy* p) {
   if (p->h_comm_status) cudaFreeHost(p->h_comm_status);
   cudaFree(p->d_norm_stats);
   cudaFree(p->d_grid_sync);
+  cudaFree(p->d_comm_dead);
   cudaFree(p->d_partials);
   cudaFree(p->d_stage);
   delete p;
@@ -570,7 +574,7 @@ int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_d
   WB_CUDA(run_mlp(p, m));
   p->comm_epoch++;
   WB_CUDA(launch_reduce_exchange(p->d_partials, grid, p->d_grads, p->peers, p->comm_rank, p->comm_world, p->comm_epoch, p->d_comm_status,
-                                 nullptr, p->stream));
+                                 p->d_comm_dead, nullptr, p->stream));
   p->launches += 2;
   return WB_OK;
 }
@@ -687,6 +691,7 @@ static int32_t train_on_device(wb_policy* p, int32_t n, TrainInputs in) {
       t.rank = p->comm_rank;
       t.epoch = ++p->comm_epoch;
       t.status = p->d_comm_status;
+      t.dead = p->d_comm_dead;
     }
     WB_CUDA(launch_mlp_tc(m, grid, p->stream, &t));
     p->launches += 1;
@@ -695,7 +700,7 @@ static int32_t train_on_device(wb_policy* p, int32_t n, TrainInputs in) {
   WB_CUDA(run_mlp(p, m));
   if (world > 1) p->comm_epoch++;
   WB_CUDA(launch_reduce_exchange(p->d_partials, grid, p->d_grads, p->peers, world > 1 ? p->comm_rank : 0, world, p->comm_epoch,
-                                 p->d_comm_status, &a, p->stream));
+                                 p->d_comm_status, p->d_comm_dead, &a, p->stream));
   p->launches += 2;
   return WB_OK;
 }

@@ -626,7 +626,7 @@ cudaError_t launch_mlp(const MlpParams& p, int grid, cudaStream_t stream) {
 // (st_release_sys / ld_acquire_sys: mlp.cuh)
 
 __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ grads,
-                                                                       ExchPeers peers, int rank, int world, uint32_t epoch, uint32_t* status,
+                                                                       ExchPeers peers, int rank, int world, uint32_t epoch, uint32_t* status, uint32_t* dead,
                                                                        AdamParams adam, int do_adam) {
   // kExchLanes threads per float4 of the slice: each sums every kExchLanes-th per-CTA partial (<= 10 independent loads in flight
   // per thread, 97 CTAs: the 3.6 MB of partials are read at memory speed instead of as 13 CTAs' dependent chains), then the
@@ -659,14 +659,21 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
   if (world > 1) {  // (world is a kernel argument: uniform)
     // a previous exchange of this handle timed out: the ranks' weights can no longer be assumed identical -- every later launch
     // is a no-op (no store, no Adam) until the host has seen the status word (wb_comm_status / wb_ppo_train_dev refuse)
-    if (__syncthreads_or(threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(status) != 0u)) return;  // (CTA-uniform)
+    // (`dead` is the DEVICE copy of the status word: reading the mapped host word from every CTA costs one PCIe round trip per
+    //  CTA, and those serialise -- ~1 us each, 100 us per exchange with 97 CTAs)
+    if (__syncthreads_or(threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(dead) != 0u)) return;  // (CTA-uniform)
     if (in) {
       // push my slice into slot [par][rank] of every rank (NVLink stores; r == rank is local); the lanes of an element share the peers
       for (int r = part; r < world; r += kExchLanes) reinterpret_cast<float4*>(peers.base[r] + exch_slot_offset(par, rank))[i4] = acc;
     }
-    __threadfence_system();
+    // the CTA's pushes are ordered before the flags by the barrier + ONE system-scope release per flag (release is cumulative over
+    // what the barrier made visible to the flag's thread).  A __threadfence_system() in every thread of every CTA -- 25 000
+    // MEMBAR.SYS per exchange -- cost ~100 us on its own.
     __syncthreads();
-    if ((int)threadIdx.x < world) st_release_sys(exch_flag(peers.base[threadIdx.x], par, rank, blockIdx.x), epoch);
+    if ((int)threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(exch_flag(peers.base[threadIdx.x], par, rank, blockIdx.x), epoch);
+    }
     bool timed_out = false;
     if ((int)threadIdx.x < world) {  // wait for rank threadIdx.x's slice in MY buffer
       const uint32_t* f = exch_flag(peers.base[rank], par, threadIdx.x, blockIdx.x);
@@ -674,6 +681,7 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
       while (ld_acquire_sys(f) != epoch) {
         if (++spins > (1L << 31)) {  // a peer never arrived (crashed?): give up loudly instead of hanging the GPU
           *reinterpret_cast<volatile uint32_t*>(status) = 1u;  // (mapped host memory: the host sees it without a copy)
+          *reinterpret_cast<volatile uint32_t*>(dead) = 1u;    // (device copy: what later launches check)
           __threadfence_system();
           timed_out = true;
           break;
@@ -705,10 +713,10 @@ __global__ void __launch_bounds__(kExchThreads) reduce_exchange_kernel(const flo
 }
 
 cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
-                                   uint32_t epoch, uint32_t* status, const AdamParams* adam, cudaStream_t stream) {
+                                   uint32_t epoch, uint32_t* status, uint32_t* dead, const AdamParams* adam, cudaStream_t stream) {
   AdamParams a{};
   if (adam) a = *adam;
-  reduce_exchange_kernel<<<kExchCtas, kExchThreads, 0, stream>>>(partials, nparts, grads, peers, rank, world, epoch, status, a, adam != nullptr);
+  reduce_exchange_kernel<<<kExchCtas, kExchThreads, 0, stream>>>(partials, nparts, grads, peers, rank, world, epoch, status, dead, a, adam != nullptr);
   return cudaGetLastError();
 }
 

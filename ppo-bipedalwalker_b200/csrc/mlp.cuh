@@ -135,12 +135,13 @@ struct FusedTail {
   ExchPeers peers;
   int32_t rank, world;
   uint32_t epoch;
-  uint32_t* status;    // mapped host word: non-zero after a time-out (every later exchange is a no-op)
+  uint32_t* status;    // mapped host word: set on a time-out (the host reads it without a copy)
+  uint32_t* dead;      // its device copy: what every later launch checks (a host-memory read per CTA would serialise over PCIe)
 };
 
 // adam != nullptr: DenseLayer.Adam is applied to the reduced gradient inside the same kernel
 cudaError_t launch_reduce_exchange(const float* partials, int nparts, float* grads, const ExchPeers& peers, int rank, int world,
-                                   uint32_t epoch, uint32_t* status, const AdamParams* adam, cudaStream_t stream);
+                                   uint32_t epoch, uint32_t* status, uint32_t* dead, const AdamParams* adam, cudaStream_t stream);
 
 // last_values: V(s_T) per environment (bootstrap of a segment that ends mid-episode) or nullptr (truncate like a trajectory end)
 cudaError_t launch_segment_returns(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int n_envs,

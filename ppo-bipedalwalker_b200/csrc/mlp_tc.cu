@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     const bool xchg = tail.world > 1;  // (kernel argument: uniform)
     // a previous exchange of this handle timed out: the ranks' weights can no longer be assumed identical -- every later launch
     // leaves the gradient buffer and the weights alone until the host has seen the status word
-    const bool dead = xchg && __syncthreads_or(tid == 0 && *reinterpret_cast<volatile uint32_t*>(tail.status) != 0u) != 0;
+    const bool dead = xchg && __syncthreads_or(tid == 0 && *reinterpret_cast<volatile uint32_t*>(tail.dead) != 0u) != 0;
     const int par = (int)(tail.epoch & 1u);
     constexpr int kLanesPer = 8;   // threads per element: each sums every 8th partial, then a butterfly (fixed order: deterministic)
     constexpr int kMaxLoads = 20;  // partials per thread kept in flight at once (8 x 20 = 160 >= the CTAs of a 148-SM grid)
@@ -860,9 +860,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
         }
       }
       if (xchg) {
-        __threadfence_system();
+        // the barrier orders the CTA's pushes before the flag threads; ONE system-scope release per flag (cumulative) publishes them
         __syncthreads();
-        if (tid < tail.world) st_release_sys(exch_flag(tail.peers.base[tid], par, tail.rank, (int)blockIdx.x), tail.epoch);
+        if (tid < tail.world) {
+          __threadfence_system();
+          st_release_sys(exch_flag(tail.peers.base[tid], par, tail.rank, (int)blockIdx.x), tail.epoch);
+        }
         bool timed_out = false;
         if (tid < tail.world) {  // wait for rank tid's slice in MY buffer
           const uint32_t* f = exch_flag(tail.peers.base[tail.rank], par, tid, (int)blockIdx.x);
@@ -870,6 +873,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
           while (ld_acquire_sys(f) != tail.epoch) {
             if (++spins > (1L << 31)) {  // a peer never arrived (crashed?): give up loudly instead of hanging the GPU
               *reinterpret_cast<volatile uint32_t*>(tail.status) = 1u;  // (mapped host memory: the host sees it without a copy)
+              *reinterpret_cast<volatile uint32_t*>(tail.dead) = 1u;
               __threadfence_system();
               timed_out = true;
               break;

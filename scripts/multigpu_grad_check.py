@@ -72,4 +72,47 @@ for variant in (0, 1):
         ok = gerr < 1e-4 and werr < 1e-5 and spread == 0.0
         print(f"{'PASS' if ok else 'FAIL'} world={world} variant={variant}: all-reduced shard gradients vs single-GPU gradient rel err {gerr:.2e}; "
               f"post-Adam weight err {werr:.2e}; weight spread across ranks {spread:.1e}", flush=True)
+# ---- the ONE-launch train step: the tensor-core gradient kernel's tail reduces, exchanges its slices over NVLink peer memory and
+#      applies Adam (wb_ppo_train_dev on a connected policy); also through the row index (wb_ppo_train_indexed_dev on the whole
+#      mini-batch, every rank picking the rows of its shard).  Six consecutive updates against the single-GPU update.
+from ppo_bipedalwalker_b200._lib import check, lib, ptr
+import ctypes as C
+one = wb.PPOAgent(hp=hp, seed=9); assert wd.connect_peers(one)
+idxd = wb.PPOAgent(hp=hp, seed=9); assert wd.connect_peers(idxd)
+two = wb.PPOAgent(hp=hp, seed=9); two.set_variant(1); assert wd.connect_peers(two)   # fp32 kernel + reduce_exchange_kernel (two launches)
+ref = wb.PPOAgent(hp=hp, seed=9)
+ref1 = wb.PPOAgent(hp=hp, seed=9); ref1.set_variant(1)  # (Adam's first steps are alpha * sign(g): compare like with like)
+a, b = wd.shard_range(n, rank, world)
+whole = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (states, actions, old, adv, ret)]
+dev = [t[a:b].contiguous() for t in whole]
+rows = torch.arange(a, b, dtype=torch.int32, device="cuda")[torch.randperm(b - a, device="cuda")]
+t1, t2 = [], []
+for rep in range(6):
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    check(lib().wb_ppo_train_dev(one._h, b - a, *[ptr(t) for t in dev]))
+    e[1].record()
+    check(lib().wb_ppo_train_dev(two._h, b - a, *[ptr(t) for t in dev]))
+    e[2].record(); e[2].synchronize()
+    t1.append(e[0].elapsed_time(e[1])); t2.append(e[1].elapsed_time(e[2]))
+    check(lib().wb_ppo_train_indexed_dev(idxd._h, b - a, ptr(rows), *[ptr(t) for t in whole]))
+    ref.TrainBatch(states, actions, old, adv, ret)
+    ref1.TrainBatch(states, actions, old, adv, ret)
+cw, failed = C.c_int32(0), C.c_int32(0)
+check(lib().wb_comm_status(one._h, C.byref(cw), C.byref(failed)))
+wr = np.concatenate([ref.actor.get_flat(), ref.critic.get_flat()])
+wr1 = np.concatenate([ref1.actor.get_flat(), ref1.critic.get_flat()])
+res = []
+for name, ag in (("one launch", one), ("one launch, indexed rows", idxd), ("fp32 kernel + exchange kernel", two)):
+    w = np.concatenate([ag.actor.get_flat(), ag.critic.get_flat()])
+    wt = torch.from_numpy(w).cuda(); wmin, wmax = wt.clone(), wt.clone()
+    dist.all_reduce(wmin, op=dist.ReduceOp.MIN); dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+    res.append((name, float(np.abs(w - (wr1 if ag is two else wr)).max()), float((wmax - wmin).abs().max())))
+if rank == 0:
+    for name, werr, spread in res:
+        # (the permuted rows change the summation order; Adam's first steps are ~alpha * sign(g), so an entry whose gradient is
+        #  within rounding of zero may move the other way: a few 1e-5 after six updates, against 1.8e-3 of total movement)
+        ok = werr < (2e-4 if 'indexed' in name else 2e-5) and spread == 0.0 and failed.value == 0
+        print(f"{'PASS' if ok else 'FAIL'} world={world} train step ({name}): weights after 6 updates vs single GPU {werr:.2e}; spread across ranks {spread:.1e}", flush=True)
+    print(f"INFO world={world} train step per mini-batch shard of {b - a}: one launch {1e3 * min(t1):.1f} us, two launches (fp32 kernel) {1e3 * min(t2):.1f} us", flush=True)
 dist.destroy_process_group()
