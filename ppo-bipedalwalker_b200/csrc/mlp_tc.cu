@@ -155,11 +155,15 @@ cudaError_t launch_tc_gemm_test(const float* A, const float* B, float* D, int M,
 //   F1   [64 x 16] x [16 x 128]   X|1  ->  A1pre | C1pre   (biases ride in the ones column)          tcgen05, K-major
 //   F2   [64 x 64] x [64 x 64]    A1   ->  A2pre                                                    tcgen05, K-major
 //        L3 (64->4, tanh), critic head (64->1), clipped-surrogate gradient, G2: registers, reference summation order
-//   one batch of three independent chains, one issuer warp each:
+//   backward, ordered so that the tensor pipe works underneath the epilogues:
 //   dW3' [128 x 64s] x [64s x 8]  [C1|A2]^T x [g3|gv]      -> dWc2, dW3 (accumulated in TMEM over all tiles)  MN-major
+//        issued as soon as [g3|gv] is staged: it executes while the epilogue warps form G2
 //   B2   [64 x 64] x [64 x 64]    G2 x W2 -> dL/dA1                                                 K-major A, MN-major B
+//        the G1 / Gc1 epilogue waits for B2 (and dW3') only ...
 //   dW2' [64 x 64s] x [64s x 96]  G2^T x [X | 1 | .. | A1] -> db2 (column 12), dW2 (columns 32..95), accumulated      MN-major
-//   dW1  [128 x 64s] x [64s x 16] [G1|Gc1]^T x [X|1]       -> dW1, db1, dWc1, dbc1 (accumulated)     MN-major
+//        ... while this one, issued behind B2 by the same thread, executes underneath that epilogue (G1 is written to the A2
+//        blocks, free once dW3' is done, so A1 stays intact for it)
+//   dW1  [128 x 64s] x [64s x 16] [Gc1|G1]^T x [X|1]       -> dWc1, dbc1, dW1, db1 (accumulated)     MN-major
 // Every MMA's descriptors are compile-time offsets from the chain's base descriptors (issue_chain_ct).  With one process the
 // kernel also reduces its per-CTA partials behind a grid barrier and applies Adam (FusedTail): Train(Batch) in ONE launch.
 // All operand tiles use the dual-use B32 layout above, fp32 accuracy via 3xTF32 (hi*hi + lo*hi + hi*lo).
@@ -182,7 +186,8 @@ struct __align__(1024) TcSmem {
   float w3[kAct * kHid], wc2[kHid], b2[kHid], b3[kAct], bc2[4];
   float mu_part[2][kS][kAct];  // the two halves' partial W3 . A2 sums
   float red[512];
-  uint64_t mbar;
+  uint64_t mbar;    // F1, F2 and the end of a tile (dW1; covers dW2 as well: same issuing thread)
+  uint64_t mbar_b;  // dW3 + B2: what the G1 / Gc1 epilogue waits for
   uint32_t tmem_slot;
 };
 
@@ -295,9 +300,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   const bool is_sample = epi && lane < 16;         // lanes 32w..32w+15 hold rows 16w..16w+15 of an M=64 accumulator
   const int s_loc = (warp & 3) * 16 + (lane & 15);
   const int lh = lane >> 4;                        // which half of the warp's column range this lane owns (16x32bx2 loads)
-  // lane 0 of warps 8..10: three MMA issuers.  A tcgen05.mma costs its issuing thread ~50 cycles of descriptor arithmetic and
-  // elect / retry bookkeeping however small the product is, so independent chains are issued from different warps; every issuer
-  // commits its own MMAs to the phase's mbarrier (3 arrivals per phase)
+  // lane 0 of warps 8..10: MMA issuers (issuer 0: F1, F2, B2, dW2', dW1; issuer 2: dW3', which overlaps the G2 epilogue).  A
+  // tcgen05.mma costs its issuing thread ~50 cycles of descriptor arithmetic and elect / retry bookkeeping however small the
+  // product is; a commit covers every MMA its thread issued before it
   const bool issuer = warp >= 8 && lane == 0;
   const int iid = warp - 8;
   const bool grad = p.mode == kModeGrad;
@@ -308,7 +313,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 #endif
   if (warp == 0) tc::tmem_alloc(&S.tmem_slot, kTmemCols);
   if (tid == 0) {
-    tc::mbar_init(&S.mbar, 3);
+    tc::mbar_init(&S.mbar, 1);
+    tc::mbar_init(&S.mbar_b, 2);
     tc::mbar_fence_init();
   }
   // ---- weights -> dual-use tiles (once per CTA).  The activation tiles and the W1 tile are cleared first (16-byte stores): every
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
   const uint32_t sm_w2_hi = tc::smem_u32(S.w2_hi), sm_w2_lo = tc::smem_u32(S.w2_lo);
   const uint32_t sm_w1_hi = tc::smem_u32(S.w1_hi), sm_w1_lo = tc::smem_u32(S.w1_lo);
   constexpr uint32_t kBlkBytes = kBlk * 4;
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase_b = 0;
 
   float lossV = 0.f, lossA = 0.f, skipped = 0.f;
   float db3_acc[kAct] = {0.f, 0.f, 0.f, 0.f}, dbc2_acc = 0.f;
@@ -463,8 +469,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     TC_MARK(0);  // P0: stage X + sync
     // ---- P1: F1 = [X|1] x [W1|b1 ; Wc1|bc1]^T  -> 128 columns
-    if (issuer) {
-      if (iid == 0) issue_chain_ct<64, 128, kKMajor, kS, kKMajor, 128, 2>(tmem + kColF1, sm_xt_hi, sm_xt_lo, sm_w1_hi, sm_w1_lo, false);
+    if (issuer && iid == 0) {
+      issue_chain_ct<64, 128, kKMajor, kS, kKMajor, 128, 2>(tmem + kColF1, sm_xt_hi, sm_xt_lo, sm_w1_hi, sm_w1_lo, false);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -507,8 +513,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
 
     TC_MARK(2);  // P2: A1 / C1 epilogue + sync
     // ---- P3: F2 = A1 x W2^T
-    if (issuer) {
-      if (iid == 0) issue_chain_ct<64, 64, kKMajor, kS, kKMajor, kHid, 8>(tmem + kColF2, sm_act_hi, sm_act_lo, sm_w2_hi, sm_w2_lo, false);
+    if (issuer && iid == 0) {
+      issue_chain_ct<64, 64, kKMajor, kS, kKMajor, kHid, 8>(tmem + kColF2, sm_act_hi, sm_act_lo, sm_w2_hi, sm_w2_lo, false);
       tc::mma_commit(&S.mbar);
     }
     if (epi) tc::mbar_wait(&S.mbar, phase);
@@ -649,7 +655,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
       const float u[8] = {g3[0], g3[1], g3[2], g3[3], gv, 0.f, 0.f, 0.f};
       store_unit(xt_hi, xt_lo, s_loc, kG3vFeature, u);
     }
-    TC_MARK(5);  // surrogate gradient + g3v staging
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    TC_MARK(5);  // surrogate gradient + g3v staging + sync
+    // ---- P5: [C1|A2]^T x [g3|gv] (dWc2, dW3) needs nothing of G2: it runs on the tensor pipe underneath the G2 epilogue
+    if (issuer && iid == 2) {
+      issue_chain_ct<128, 8, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW3, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes,
+                                                            sm_xt_hi + kG3vFeature * 4, sm_xt_lo + kG3vFeature * 4, any_tile);
+      tc::mma_commit(&S.mbar_b);
+    }
     // dL/dz2 = (W3^T g3) * leaky'(z2) for the half's 32 columns (sum over k from 0, Matrix.Multiply order).  G2 has its own
     // tile, so nothing here waits for the dW3 product (which reads A2): it is issued together with the G2 products below.
     if (epi) {
@@ -676,25 +692,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     tc::fence_after_thread_sync();
 
     TC_MARK(7);  // G2 epilogue + sync
-    // ---- P5/P6 in one batch: [C1|A2]^T x [g3|gv] (dWc2, dW3) ; dL/dA1 = G2 x W2 ; G2^T x [X | 1 | .. | A1] (db2, dW2)
-    if (issuer) {
-      if (iid == 2)
-        issue_chain_ct<128, 8, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW3, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes,
-                                                              sm_xt_hi + kG3vFeature * 4, sm_xt_lo + kG3vFeature * 4, any_tile);
-      if (iid == 0) issue_chain_ct<64, 64, kKMajor, kS, kMnMajor, kHid, 8>(tmem + kColB2, sm_g2_hi, sm_g2_lo, sm_w2_hi, sm_w2_lo, false);
-      if (iid == 1) issue_chain_ct<64, 96, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW2, sm_g2_hi, sm_g2_lo, sm_xt_hi, sm_xt_lo, any_tile);
-      tc::mma_commit(&S.mbar);
+    // ---- P6: dL/dA1 = G2 x W2 first (the G1 epilogue waits for it, and for dW3 above), then G2^T x [X | 1 | .. | A1] (db2, dW2)
+    //      from the same thread: it executes underneath the G1 / Gc1 epilogue, which no longer overwrites what it reads (G1 goes
+    //      to the A2 blocks, free once dW3 is done), and is covered by the commit behind dW1
+    if (issuer && iid == 0) {
+      issue_chain_ct<64, 64, kKMajor, kS, kMnMajor, kHid, 8>(tmem + kColB2, sm_g2_hi, sm_g2_lo, sm_w2_hi, sm_w2_lo, false);
+      tc::mma_commit(&S.mbar_b);
+      issue_chain_ct<64, 96, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW2, sm_g2_hi, sm_g2_lo, sm_xt_hi, sm_xt_lo, any_tile);
     }
-    if (epi) tc::mbar_wait(&S.mbar, phase);
-    phase ^= 1;
+    if (epi) tc::mbar_wait(&S.mbar_b, phase_b);
+    phase_b ^= 1;
     __syncwarp();
     tc::fence_after_thread_sync();
 
     TC_MARK(8);  // P6: B2 / dW2 / dB2 MMA + wait
-    // ---- P7: half 0: G1 = dL/dA1 * leaky'(z1) -> overwrites A1; half 1: Gc1 = (Wc2^T gv) * leaky'(zc1) -> overwrites C1
+    // ---- P7: half 0: G1 = dL/dA1 * leaky'(z1) -> the A2 blocks (A1 is still being read by the dW2 product); half 1:
+    //      Gc1 = (Wc2^T gv) * leaky'(zc1) -> overwrites C1.  Blocks 3..6 then hold [Gc1 | G1], the 128-row operand of dW1.
     if (epi) {
-      float* hi_t = act_hi + half * 2 * kBlk;
-      float* lo_t = act_lo + half * 2 * kBlk;
+      float* hi_t = act_hi + (half == 0 ? 4 : 2) * kBlk;
+      float* lo_t = act_lo + (half == 0 ? 4 : 2) * kBlk;
       const int cb = lh * 32;  // my 32 columns (the ones mask1 describes)
       float v[32];
       if (half == 0) {
@@ -715,9 +731,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
     tc::fence_after_thread_sync();
 
     TC_MARK(9);  // P7: G1 / Gc1 epilogue + sync
-    // ---- P8: [G1|Gc1]^T x [X|1]  (accumulates dW1, db1, dWc1, dbc1)
-    if (issuer) {
-      if (iid == 0) issue_chain_ct<128, 16, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW1, sm_act_hi, sm_act_lo, sm_xt_hi, sm_xt_lo, any_tile);
+    // ---- P8: [Gc1|G1]^T x [X|1]  (accumulates dWc1, dbc1, dW1, db1); its commit also covers the dW2 product issued above
+    if (issuer && iid == 0) {
+      issue_chain_ct<128, 16, kMnMajor, kS, kMnMajor, kS, 8>(tmem + kColDW1, sm_act_hi + 2 * kBlkBytes, sm_act_lo + 2 * kBlkBytes, sm_xt_hi,
+                                                             sm_xt_lo, any_tile);
       tc::mma_commit(&S.mbar);
     }
     tc::mbar_wait(&S.mbar, phase);  // EVERY warp (the issuer warps stage X too): the next tile overwrites the X block and the tiles dW1 reads
@@ -758,13 +775,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) ppo_tc_kernel(const MlpParams p
         tc::tmem_ld_wait();
         if (is_sample) out[kOffB2 + s_loc] = v[12];
       }
-      // dW1|db1 (rows 0..63) and dWc1|dbc1 (rows 64..127): M = 128, row = thread
+      // dWc1|dbc1 (rows 0..63) and dW1|db1 (rows 64..127): M = 128, row = thread
       {
         float v[16];
         tc::tmem_ld_x16(tmem_warp + kColDW1, v);
         tc::tmem_ld_wait();
         const int o = tid & 63;
-        const int offW = tid < 64 ? kOffW1 : kOffWc1, offB = tid < 64 ? kOffB1 : kOffBc1;
+        const int offW = tid < 64 ? kOffWc1 : kOffW1, offB = tid < 64 ? kOffBc1 : kOffB1;
         float4* dst = reinterpret_cast<float4*>(out + offW + o * kIn);  // 12 consecutive floats, 48-byte rows: 16-byte aligned
 #pragma unroll
         for (int j = 0; j < 3; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
