@@ -159,9 +159,9 @@ public sealed class GpuPPOAgent : IDisposable
                     badv[b] = advantages[idx];
                     bret[b] = returns[idx];
                 }
-                // Train(Batch) (:218-346): Zero, per-sample clipped-surrogate + value gradients, FeedBack, Optimise
-                if (Wb.Ok(Wb.wb_ppo_grad(_policy, B, bs, ba, bl, badv, bret, losses, out _), "wb_ppo_grad"))
-                    Wb.Ok(Wb.wb_adam_step(_policy), "wb_adam_step");
+                // Train(Batch) (:218-346): Zero, per-sample clipped-surrogate + value gradients, FeedBack, Optimise -- one call,
+                // one kernel launch on the default networks (wb_ppo_grad + wb_adam_step are the two halves)
+                Wb.Ok(Wb.wb_ppo_train(_policy, B, bs, ba, bl, badv, bret, losses, out _), "wb_ppo_train");
                 renderer.UpdateConsole(epoch, j, batchCount, losses[0]);
             }
         }
