@@ -957,6 +957,15 @@ cudaError_t launch_mlp_tc(const MlpParams& p, int grid, cudaStream_t stream, con
   gc.variance = gc.stdv * gc.stdv;
   FusedTail t{};
   if (tail) t = *tail;
+  if (t.enabled) {
+    // the tail's grid barrier needs every CTA resident at once: a cooperative launch makes the driver guarantee it (two such
+    // kernels on different streams, or from different processes under MPS, are then run one after the other instead of each
+    // holding half of the SMs and waiting for the rest)
+    MlpParams p_arg = p;
+    void* args[3] = {&p_arg, &gc, &t};
+    const void* fn = p.index ? reinterpret_cast<const void*>(ppo_tc_kernel<true>) : reinterpret_cast<const void*>(ppo_tc_kernel<false>);
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kTcThreads), args, sizeof(TcSmem), stream);
+  }
   if (p.index)
     ppo_tc_kernel<true><<<grid, kTcThreads, sizeof(TcSmem), stream>>>(p, gc, t);
   else

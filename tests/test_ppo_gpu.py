@@ -437,6 +437,37 @@ def test_host_train_step_reads_pinned_buffers_in_place(gpu, O):
             np.testing.assert_allclose(a, {"actor": actor, "critic": critic}[which].get_params(), rtol=0, atol=3e-5)
 
 
+@pytest.mark.timeout(120)
+def test_two_policies_on_two_streams_train_concurrently(gpu):
+    """The one-launch train step holds a grid barrier, so every CTA must be resident at once: it is a COOPERATIVE launch, and two
+    policies that train on different streams are run one after the other by the driver instead of deadlocking with half of the
+    SMs each.  Their results equal the same updates issued on one stream."""
+    import torch
+    from ppo_bipedalwalker_b200._lib import check, lib, ptr
+    n = 65536
+    hp = gpu.default_hyperparams()
+    hp.batch_size = n
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    a1, a2 = gpu.PPOAgent(hp=hp, seed=1, stream=s1.cuda_stream), gpu.PPOAgent(hp=hp, seed=2, stream=s2.cuda_stream)
+    b1, b2 = gpu.PPOAgent(hp=hp, seed=1), gpu.PPOAgent(hp=hp, seed=2)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    dev = [torch.randn(n, 12, device="cuda", generator=g), 0.3 * torch.randn(n, 4, device="cuda", generator=g),
+           -0.5 * torch.rand(n, 4, device="cuda", generator=g), torch.randn(n, device="cuda", generator=g),
+           torch.randn(n, device="cuda", generator=g)]
+    torch.cuda.synchronize()
+    for _ in range(40):
+        check(lib().wb_ppo_train_dev(a1._h, n, *[ptr(t) for t in dev]))
+        check(lib().wb_ppo_train_dev(a2._h, n, *[ptr(t) for t in dev]))
+    for _ in range(40):
+        check(lib().wb_ppo_train_dev(b1._h, n, *[ptr(t) for t in dev]))
+    for _ in range(40):
+        check(lib().wb_ppo_train_dev(b2._h, n, *[ptr(t) for t in dev]))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(a1.actor.get_flat(), b1.actor.get_flat())
+    np.testing.assert_array_equal(a2.critic.get_flat(), b2.critic.get_flat())
+
+
 def test_topologies_outside_the_kernels_fail_loudly(gpu):
     with pytest.raises(gpu.WalkerB200Error):  # wider than the 128 the kernels cover: refused, never a silent fallback
         gpu.PPOAgent(actor="Input |256| (ReLU) |4| (TanH) Output")
