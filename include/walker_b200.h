@@ -298,8 +298,9 @@ int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const
 int32_t wb_ppo_train_indexed_dev(wb_policy* p, int32_t n, const int32_t* index_dev, const float* states_pool, const float* actions_pool,
                                  const float* logp_pool, const float* advantages_pool, const float* returns_pool);
 /* PPOAgent.Train(Batch) from host buffers: wb_ppo_grad + wb_adam_step as one call (one launch on the default path).  When all five
- * buffers are page-locked (cudaHostAlloc / cudaHostRegister / wb_host_pin) and 16-byte aligned the kernel reads them in place over
- * PCIe while it computes (no staging copy); wb_ppo_grad takes the same zero-copy path.  losses / skipped as wb_ppo_grad. */
+ * buffers are page-locked (cudaHostAlloc / cudaHostRegister / wb_host_pin) and 16-byte aligned the tensor-core kernel reads them in
+ * place over PCIe while it computes (no staging copy); wb_ppo_grad takes the same zero-copy path; the other kernel variants and
+ * pageable buffers are staged.  losses / skipped as wb_ppo_grad. */
 int32_t wb_ppo_train(wb_policy* p, int32_t n, const float* states_host, const float* actions_host, const float* old_logp_host,
                      const float* advantages_host, const float* returns_host, float* losses_host, int32_t* skipped_host);
 /* NeuralNetwork.Optimise -> DenseLayer.Adam on both networks (NeuralNetwork.cs:85-91, DenseLayer.cs:125-159) */

@@ -724,7 +724,8 @@ static int32_t minibatch_on_device(wb_policy* p, int32_t n, const float* states_
   const size_t IN = (size_t)p->actor.input, ACT = (size_t)p->actor.output;
   const size_t N = (size_t)n;
   static const bool zero_copy_enabled = getenv("WB_NO_ZERO_COPY") == nullptr;
-  if (zero_copy_enabled) {
+  // (only the tensor-core kernel streams every input exactly once through a prefetch that hides the PCIe latency)
+  if (zero_copy_enabled && !use_generic(p) && p->variant == 0) {
     const float* s = static_cast<const float*>(device_alias_of_pinned(states_host, sizeof(float) * N * IN));
     const float* a = static_cast<const float*>(device_alias_of_pinned(actions_host, sizeof(float) * N * ACT));
     const float* l = static_cast<const float*>(device_alias_of_pinned(old_logp_host, sizeof(float) * N * ACT));
