@@ -1224,6 +1224,74 @@ __device__ __noinline__ void integrate_body(int col, int b, float dt) {
 }
 
 
+// Joints: every thread runs Joint.Step for its OWN walker's four joints, in creation order, instead of three queue rounds.  A joint
+// needs correcting in ~20 % of the substeps and its chain is short (~120 instructions), so a warp executes all four chains at
+// 20 % lane density -- more issued instructions than the dense drain (+6 %), but three rounds (six barriers, three waits for
+// the slowest warp) fewer per substep: 262144 walkers 4.26 -> 4.05 ms per env-step (profiles/ab_experiments_r2.log).
+// -DWB_JOINTS_INTHREAD=0 restores the queue rounds; =2 merges joints 1 and 2 (disjoint bodies) into one function with two
+// independent instruction streams (measured slower: 4.23 ms).
+#ifndef WB_JOINTS_INTHREAD
+#define WB_JOINTS_INTHREAD 1
+#endif
+template <int kE>
+__device__ __noinline__ void joint_in_thread(int col, int k) {
+  Env<1, kE> e;
+  env_for_column(e, shm<kE>(), col, true);
+  const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
+  joint_step<Env<1, kE>, false>(e, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, nullptr);
+}
+
+// joints (Body, RLU) and (LLU, LLL) -- k = 1, 2 -- touch disjoint bodies: one early-out for both and two independent instruction
+// streams in one function (-DWB_JOINTS_INTHREAD=2)
+template <int kE>
+__device__ __noinline__ void joint_pair_in_thread(int col) {
+  using EV = Env<1, kE>;
+  EV e;
+  env_for_column(e, shm<kE>(), col, true);
+  struct J {
+    int A, ia, B, ib;
+    float2 pA, pB, ab;
+    float depth;
+    bool active;
+  } j[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int k = q + 1;
+    j[q].A = (0x4122 >> (4 * k)) & 0xF;
+    j[q].B = (0x3041 >> (4 * k)) & 0xF;
+    j[q].ia = k < 2 ? 1 : 2;
+    j[q].ib = k < 2 ? 4 : 3;
+    j[q].pA = V2(e, j[q].A * 6 + j[q].ia);
+    j[q].pB = V2(e, j[q].B * 6 + j[q].ib);
+    j[q].ab = vsub(j[q].pB, j[q].pA);
+    j[q].depth = fsqrt(fadd(fmul(j[q].ab.x, j[q].ab.x), fmul(j[q].ab.y, j[q].ab.y)));
+    j[q].active = !(j[q].depth < 0.1f);
+  }
+  if (!__any_sync(kFull, j[0].active || j[1].active)) return;
+  float2 n[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) n[q] = vnormalize_fast(j[q].ab);
+#pragma unroll
+  for (int q = 0; q < 2; q++) {  // Joint.Step, Joint.cs:31-41 (see joint_step above)
+    const float2 dA = vhalf(vmul(n[q], j[q].depth));
+    const float2 dB = vhalf(vmul(vneg(n[q]), j[q].depth));
+    BodyDyn X = load_dyn(e, j[q].B);
+    BodyDyn Y = load_dyn(e, j[q].A);
+    move_bodies<EV, 1>(e, j[q].active, j[q].A, dA, true, j[q].B, dB);
+    X.c = vadd(X.c, dB);
+    Y.c = vadd(Y.c, dA);
+    const float2 contact = vhalf(vadd(vadd(j[q].pA, dA), vadd(j[q].pB, dB)));
+    float2 rX, rY;
+    float imp;
+    calculate_impulse(X, Y, contact, fadd(1.0f, 1.0f), n[q], rX, rY, imp);
+    apply_impulses(X, Y, n[q], imp, rX, rY);
+    if (j[q].active) {
+      store_dyn(e, j[q].B, X);
+      store_dyn(e, j[q].A, Y);
+    }
+  }
+}
+
 enum { kItemPole = 0, kItemFloor = 1, kItemJoint = 2 };
 // SAT rounds of the queued items: 16 items share a warp, so an early stop (all of them separated) practically never happens
 #ifndef WB_DRAIN_VOTE
@@ -1235,15 +1303,21 @@ constexpr int kDrainVote = WB_DRAIN_VOTE;
 // like the L > 1 layouts of the plain kernel; with ~15-20 % of the walkers queued per round this keeps most warps of the CTA
 // busy and roughly halves the latency of the round).  Item = walker column | payload << 10.
 constexpr int kG = 2;
+// lanes per FLOOR item (-DWB_FLOOR_G=4, experiment): a floor round queues few items (~27 of 256 walkers), so wider groups still
+// fit one pass and shorten its SAT (10 axes: 5 rounds with two lanes, 3 with four)
+#ifndef WB_FLOOR_G
+#define WB_FLOOR_G 2
+#endif
+constexpr int kGFloor = WB_FLOOR_G;
 
-template <int kE>
-__device__ __forceinline__ void group_env_for_column(Env<kG, kE>& e, Shared<kE>& S, int col, bool live) {
+template <int G, int kE>
+__device__ __forceinline__ void group_env_for_column(Env<G, kE>& e, Shared<kE>& S, int col, bool live) {
   e.v2 = reinterpret_cast<float2*>(S.state) + col;
   e.f = S.state + kV2Count * kE * 2 + col;
   e.fl = &S.floor;
-  e.sub = threadIdx.x % kG;
+  e.sub = threadIdx.x % G;
   e.gsub = e.sub;
-  e.gshift = ((threadIdx.x & 31) / kG) * kG;
+  e.gshift = ((threadIdx.x & 31) / G) * G;
   e.live = live;
   e.flags = 0;
   set_materials(e, S.mtab[S.wmat[col]], S.mtab[S.fmat[col]]);
@@ -1252,24 +1326,25 @@ __device__ __forceinline__ void group_env_for_column(Env<kG, kE>& e, Shared<kE>&
 template <int KIND, int kE>
 __device__ __noinline__ void drain(int parity) {
   Shared<kE>& S = shm<kE>();
-  using EVG = Env<kG, kE>;
+  constexpr int G = KIND == kItemFloor ? kGFloor : kG;
+  using EVG = Env<G, kE>;
   const int count = S.count[parity];
-  const int warp_base = (threadIdx.x >> 5) * (32 / kG), lane = threadIdx.x & 31;
+  const int warp_base = (threadIdx.x >> 5) * (32 / G), lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int base = warp_base; base < count; base += kE / kG) {
-    const int slot = base + lane / kG;
+  for (int base = warp_base; base < count; base += kE / G) {
+    const int slot = base + lane / G;
     const bool valid = slot < count;
     const int item = valid ? S.queue[slot] : 0;
     const int col = item & 1023, payload = item >> 10;
     EVG q;
-    group_env_for_column(q, S, col, valid);
+    group_env_for_column<G, kE>(q, S, col, valid);
     if (KIND == kItemPole) {
       int sep_axis = -1;
-      resolve_pair<EVG, kG, false, false, kDrainVote, true>(q, valid, payload, partner_of(payload), nullptr, &sep_axis);
+      resolve_pair<EVG, G, false, false, kDrainVote, true>(q, valid, payload, partner_of(payload), nullptr, &sep_axis);
       // the lane that saw the lowest separating axis of the group records it (any separating axis is a valid cache entry)
       if (valid && sep_axis >= 0) S.axis[pair_slot(payload) * kE + col] = (unsigned char)sep_axis;
     } else if (KIND == kItemFloor) {
-      resolve_pair<EVG, kG, false, true, kDrainVote, true>(q, valid, payload, FLOOR, nullptr);
+      resolve_pair<EVG, G, false, true, kDrainVote, true>(q, valid, payload, FLOOR, nullptr);
     } else {
       const int k = payload;
       const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
@@ -1396,6 +1471,9 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
       long long t_arr0 = prof_clock();
       if ((tid & 31) == 0) S.prof_arrive[parity][0][pw] = t_arr0;
 #endif
+      // (the other counter was last read by the previous round's drain, which ended behind that round's second barrier: it can be
+      //  cleared before this round's first barrier, and the next round's pushes find it cleared whether or not the second one runs)
+      if (tid == 0) S.count[parity ^ 1] = 0;
       scope_sync<kE>();
 #ifdef WB_PHASE_PROFILE
       long long last0 = 0;
@@ -1404,8 +1482,12 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
       prof_acc[1] += (unsigned long long)(last0 - t_arr0);   // wait before the drain
       prof_items += S.count[parity];
       prof_rounds++;
+#else
+      if (S.count[parity] == 0) {  // nothing queued (the upper legs' floor round, most of the time): no drain, no second barrier
+        parity ^= 1;
+        return;
+      }
 #endif
-      if (tid == 0) S.count[parity ^ 1] = 0;
       drain_fn();
 #ifdef WB_PHASE_PROFILE
       long long t_arr1 = prof_clock();
@@ -1424,6 +1506,13 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
 
 #pragma unroll 1
     for (int it = 0; it < p.iterations; it++) {
+#if WB_JOINTS_INTHREAD == 2
+      joint_in_thread<kE>(tid, 0);
+      joint_pair_in_thread<kE>(tid);
+      joint_in_thread<kE>(tid, 3);
+#elif WB_JOINTS_INTHREAD
+      for (int k = 0; k < 4; k++) joint_in_thread<kE>(tid, k);
+#else
       // ---- joints in creation order; (Body,RLU) and (LLU,LLL) touch disjoint bodies and share a round
       push(S, parity, joint_gap_active(0), tid | (0 << 10));
       round([&] { drain<kItemJoint, kE>(parity); });
@@ -1432,6 +1521,7 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
       round([&] { drain<kItemJoint, kE>(parity); });
       push(S, parity, joint_gap_active(3), tid | (3 << 10));
       round([&] { drain<kItemJoint, kE>(parity); });
+#endif
       // ---- body sweep: {LLL, RLL, Body}, then {LLU, RLU}; per leg segment [floor if floor-first] [leg partner] [floor if
       //      floor-last].  The Body only ever meets the floor (Walker.cs:204-209), so its step is independent of both legs during
       //      the sweep: it is integrated with the first pair and its floor item rides in that pair's first floor round instead
