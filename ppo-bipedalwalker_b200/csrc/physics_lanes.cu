@@ -1353,6 +1353,37 @@ __device__ __noinline__ void drain(int parity) {
   }
 }
 
+// The upper legs' floor round (second leg phase) is sparse: an upper leg only reaches the floor when the walker has fallen, ~2.5
+// items per 256 walkers and substep, yet as a queue round it costs every warp of the CTA two barriers and the wait for one full
+// floor chain.  -DWB_F1_INWARP=1: the owning WARP resolves its own items instead (8 lanes per item, four items per pass; the
+// state columns are in shared memory, so any lane can work on any walker of the warp), no CTA barrier; warps without an item --
+// most of them -- skip the stage on a single vote.
+#ifndef WB_F1_INWARP
+#define WB_F1_INWARP 0
+#endif
+template <int kE>
+__device__ __noinline__ void warp_floor_items(bool f0, int b0, bool f1, int b1) {
+  const unsigned m0 = __ballot_sync(kFull, f0), m1 = __ballot_sync(kFull, f1);
+  if ((m0 | m1) == 0u) return;
+  __syncwarp();  // the owners' integration writes are visible to the lanes that take their walkers
+  Shared<kE>& S = shm<kE>();
+  constexpr int G = 8;
+  using EVG = Env<G, kE>;
+  const int lane = threadIdx.x & 31, col0 = threadIdx.x & ~31;
+  const int n0 = __popc(m0), total = n0 + __popc(m1);
+#pragma unroll 1
+  for (int base = 0; base < total; base += 32 / G) {
+    const int idx = base + lane / G;  // items: the b0 bodies in lane order, then the b1 bodies (all independent of each other)
+    const bool valid = idx < total;
+    const bool first = idx < n0;
+    const unsigned src = valid ? __fns(first ? m0 : m1, 0, (first ? idx : idx - n0) + 1) : 0u;
+    EVG q;
+    group_env_for_column<G, kE>(q, S, col0 + (int)src, valid);
+    resolve_pair<EVG, G, false, true, -1, true>(q, valid, first ? b0 : b1, FLOOR, nullptr);
+  }
+  __syncwarp();
+}
+
 template <int kE>
 __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)) physics_compact_kernel(const PhysicsParams p) {
   using EV = Env<1, kE>;
@@ -1537,15 +1568,19 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
         if (any_first) {
           const bool f0 = floor_first && floor_pair_needs_work<kE>(tid, b0), f1 = floor_first && floor_pair_needs_work<kE>(tid, b1);
           e.flags |= (f0 ? 1 << b0 : 0) | (f1 ? 1 << b1 : 0);
-          push(S, parity, f0, tid | (b0 << 10));
-          push(S, parity, f1, tid | (b1 << 10));
-          if (body_pending) {
-            const bool fb = floor_pair_needs_work<kE>(tid, BODY);
-            if (fb) e.flags |= 1 << BODY;
-            push(S, parity, fb, tid | (BODY << 10));
-            body_pending = false;
+          if (WB_F1_INWARP && ph == 1) {
+            warp_floor_items<kE>(f0, b0, f1, b1);
+          } else {
+            push(S, parity, f0, tid | (b0 << 10));
+            push(S, parity, f1, tid | (b1 << 10));
+            if (body_pending) {
+              const bool fb = floor_pair_needs_work<kE>(tid, BODY);
+              if (fb) e.flags |= 1 << BODY;
+              push(S, parity, fb, tid | (BODY << 10));
+              body_pending = false;
+            }
+            round([&] { drain<kItemFloor, kE>(parity); });
           }
-          round([&] { drain<kItemFloor, kE>(parity); });
         }
         push(S, parity, pole_pair_needs_work<kE>(tid, b0, partner_of(b0)), tid | (b0 << 10));
         push(S, parity, pole_pair_needs_work<kE>(tid, b1, partner_of(b1)), tid | (b1 << 10));
