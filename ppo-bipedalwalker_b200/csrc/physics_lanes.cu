@@ -1222,6 +1222,46 @@ __device__ __noinline__ void integrate_body(int col, int b, float dt) {
   env_for_column(e, shm<kE>(), col, true);
   integrate_body_inl(e, b, dt);
 }
+// the same, and the bounding-box test against the floor on the NEW vertices while they are still in registers (what
+// floor_pair_needs_work would reload and recompute right afterwards for a floor-first walker); -DWB_FUSED_FLOOR_TEST=0: separate calls
+#ifndef WB_FUSED_FLOOR_TEST
+#define WB_FUSED_FLOOR_TEST 1
+#endif
+template <int kE>
+__device__ __noinline__ bool integrate_body_floor_test(int col, int b, float dt) {
+  Env<1, kE> e;
+  env_for_column(e, shm<kE>(), col, true);
+  float2 v = V2(e, kV2Vel + b);
+  v = vadd(v, vmul(mk2(0.0f, 980.0f), dt));
+  const float2 d = vmul(v, dt);
+  const float w = F1(e, kFOmega + b);
+  const float theta = fmul(w, dt);
+  float ang = fadd(F1(e, kFAngle + b), theta);
+  const float PI_F = 3.14159274f, TAU_F = 6.28318548f;
+  if (ang > PI_F) ang = fsub(ang, TAU_F);
+  else if (ang < -PI_F) ang = fadd(ang, TAU_F);
+  float m11, m12;
+  rotz(theta, m11, m12);
+  const float m21 = -m12, m22 = m11;
+  const float2 cen = vadd(V2(e, kV2Cen + b), d);
+  float2 P[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float2 p = vadd(V2(e, b * 6 + i), d);
+    p = vsub(p, cen);
+    float2 t;
+    t.x = fadd(fadd(fmul(p.x, m11), fmul(p.y, m21)), 0.0f);
+    t.y = fadd(fadd(fmul(p.x, m12), fmul(p.y, m22)), 0.0f);
+    P[i] = vadd(t, cen);
+    V2(e, b * 6 + i) = P[i];
+  }
+  V2(e, kV2Cen + b) = cen;
+  V2(e, kV2Vel + b) = v;
+  F1(e, kFAngle + b) = ang;
+  float2 amin, amax;
+  aabb6(P, amin, amax);
+  return aabb_hit(amin, amax, e.fl->bb_min, e.fl->bb_max);
+}
 
 
 // Joints: every thread runs Joint.Step for its OWN walker's four joints, in creation order, instead of three queue rounds.  A joint
@@ -1561,12 +1601,22 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
       for (int ph = 0; ph < 2; ph++) {
         const int b0 = ph == 0 ? LLL : LLU;
         const int b1 = ph == 0 ? RLL : RLU;
+        bool body_pending = ph == 0;
+#if WB_FUSED_FLOOR_TEST
+        const bool hit0 = integrate_body_floor_test<kE>(tid, b0, dt);
+        const bool hit1 = integrate_body_floor_test<kE>(tid, b1, dt);
+        const bool hitb = body_pending && integrate_body_floor_test<kE>(tid, BODY, dt);  // (ph is uniform: no divergent call)
+#else
         integrate_body<kE>(tid, b0, dt);
         integrate_body<kE>(tid, b1, dt);
-        bool body_pending = ph == 0;
         if (body_pending) integrate_body<kE>(tid, BODY, dt);
+#endif
         if (any_first) {
+#if WB_FUSED_FLOOR_TEST
+          const bool f0 = floor_first && hit0, f1 = floor_first && hit1;
+#else
           const bool f0 = floor_first && floor_pair_needs_work<kE>(tid, b0), f1 = floor_first && floor_pair_needs_work<kE>(tid, b1);
+#endif
           e.flags |= (f0 ? 1 << b0 : 0) | (f1 ? 1 << b1 : 0);
           if (WB_F1_INWARP && ph == 1) {
             warp_floor_items<kE>(f0, b0, f1, b1);
@@ -1574,7 +1624,11 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
             push(S, parity, f0, tid | (b0 << 10));
             push(S, parity, f1, tid | (b1 << 10));
             if (body_pending) {
+#if WB_FUSED_FLOOR_TEST
+              const bool fb = hitb;
+#else
               const bool fb = floor_pair_needs_work<kE>(tid, BODY);
+#endif
               if (fb) e.flags |= 1 << BODY;
               push(S, parity, fb, tid | (BODY << 10));
               body_pending = false;
