@@ -1097,6 +1097,7 @@ struct Shared {
   FloorConst floor;
   unsigned char axis[4 * kE];   // last separating axis per ordered leg pair {LLL->LLU, LLU->LLL, RLL->RLU, RLU->RLL}
   unsigned short queue[3 * kE];  // a floor round holds at most three items per walker (two leg segments + the Body)
+  unsigned char jq[4 * kE];      // per-warp item lists of the compacted joint passes (128 slots per warp: lane | joint << 5)
   int count[2];  // ping-pong: the counter of the next round is cleared while the current one drains
   unsigned long long stage_bar;  // mbarrier of the bulk-copy staging
 #ifdef WB_PHASE_PROFILE
@@ -1329,6 +1330,59 @@ __device__ __noinline__ void joint_pair_in_thread(int col) {
       store_dyn(e, j[q].B, X);
       store_dyn(e, j[q].A, Y);
     }
+  }
+}
+
+// -DWB_JOINTS_INTHREAD=3: the four joints of a warp's 32 walkers as warp-level passes.  The reference steps the joints in creation
+// order, but two joints only depend on each other through a shared body AND only if the earlier one is active (an inactive joint
+// changes nothing): joint 1 (Body, RLU) and joint 2 (LLU, LLL) wait for joint 0 (Body, LLU), joint 3 (RLU, RLL) waits for joint 1.
+// Every pass the owning lane tests the joints of its walker whose predecessor is settled (inactive, or processed in an earlier
+// pass); the active ones of the whole warp -- on average 0.68 x 32 in the first pass -- are listed in shared memory and each
+// lane runs ONE of them (any lane can work on any walker of the warp: the state is in shared-memory columns).  Two or three
+// executions of the ~200-instruction correction per substep instead of four, bit-identical results.
+template <int kE>
+__device__ __noinline__ void joints_compacted(int col) {
+  using EV = Env<1, kE>;
+  Shared<kE>& S = shm<kE>();
+  EV own;
+  env_for_column(own, S, col, true);
+  const int lane = col & 31, col0 = col & ~31;
+  unsigned char* list = S.jq + 4 * col0;
+  unsigned todo = 0xFu;
+#pragma unroll 1
+  while (__any_sync(kFull, todo != 0u)) {
+    unsigned act = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int pred = k == 3 ? 1 : 0;
+      if (((todo >> k) & 1u) && (k == 0 || !((todo >> pred) & 1u))) {
+        const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
+        const float2 ab = vsub(V2(own, B * 6 + (k < 2 ? 4 : 3)), V2(own, A * 6 + (k < 2 ? 1 : 2)));
+        const float depth = fsqrt(fadd(fmul(ab.x, ab.x), fmul(ab.y, ab.y)));
+        if (!(depth < 0.1f)) act |= 1u << k;   // stays in todo until it has been processed
+        else todo &= ~(1u << k);               // inactive: settled, its successors may be tested in this very pass
+      }
+    }
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned m = __ballot_sync(kFull, (act >> k) & 1u);
+      if ((act >> k) & 1u) list[total + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(lane | (k << 5));
+      total += __popc(m);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int base = 0; base < total; base += 32) {
+      const bool valid = base + lane < total;
+      const int item = valid ? list[base + lane] : 0;
+      const int k = item >> 5;
+      EV e;
+      env_for_column(e, S, col0 + (item & 31), valid);
+      const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
+      joint_step<EV, false>(e, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, nullptr);
+    }
+    __syncwarp();  // the corrections are visible to the owners' next tests; the list may be rewritten
+    todo &= ~act;
   }
 }
 
@@ -1577,7 +1631,9 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
 
 #pragma unroll 1
     for (int it = 0; it < p.iterations; it++) {
-#if WB_JOINTS_INTHREAD == 2
+#if WB_JOINTS_INTHREAD == 3
+      joints_compacted<kE>(tid);
+#elif WB_JOINTS_INTHREAD == 2
       joint_in_thread<kE>(tid, 0);
       joint_pair_in_thread<kE>(tid);
       joint_in_thread<kE>(tid, 3);
