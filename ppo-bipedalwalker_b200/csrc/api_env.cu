@@ -161,9 +161,11 @@ static int default_lanes(int n_envs, int sm_count) {
   if (per_sm <= 10) return 32;   // a handful of walkers (the reference's single-walker case): all 32 lanes on one walker
   if (per_sm <= 22) return 16;   // 2048 walkers: 0.315 ms (16) vs 0.325 (8) / 0.345 (32); 3072: 0.359 vs 0.366
   if (per_sm <= 48) return 8;    // 4096: 0.375 (8) vs 0.416 (16) / 0.446 (4); 7104: 0.438 vs 0.510 (4)
-  if (per_sm <= 150) return 4;   // 8192: 0.508 (4) vs 0.688 (8); 16384: 0.725 vs 0.784 (2) / 0.945 (compacting)
-  if (per_sm <= 200) return 2;   // 23680: 0.900 (2) vs 1.075 (4); 28416: 0.937 vs 0.963 (compacting)
-  return 1001;  // GPU full: one thread per walker with CTA-level work compaction (32768: 0.968 vs 1.092 (2))
+  // (second sweep of round 2, after the compacting kernel lost its joint rounds -- appended to profiles/variant_sweep_r2.log: the
+  //  2-lane layout no longer wins anywhere, and between ~125 and ~375 walkers per SM four CTAs of 128 walkers beat two of 256)
+  if (per_sm <= 124) return 4;   // 8192: 0.508 (4) vs 0.688 (8); 16384: 0.727 (4) vs 0.782 (1003) / 0.784 (2)
+  if (per_sm <= 375) return 1003;  // 20480: 0.843 (1003) vs 0.895 (2) / 1.027 (4); 32768: 0.912 vs 0.948 (1001); 53248: 1.073 vs 1.134 (1001)
+  return 1001;  // GPU full: scopes of 256 walkers, two CTAs per SM (57344: 1.142 vs 1.172 (1003); 262144: 3.98 vs 4.38)
 }
 
 struct wb_env_batch {
