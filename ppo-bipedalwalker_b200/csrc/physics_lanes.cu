@@ -1281,6 +1281,14 @@ __device__ __noinline__ void joint_in_thread(int col, int k) {
   const int A = (0x4122 >> (4 * k)) & 0xF, B = (0x3041 >> (4 * k)) & 0xF;
   joint_step<Env<1, kE>, false>(e, A, k < 2 ? 1 : 2, B, k < 2 ? 4 : 3, nullptr);
 }
+// the same with the joint index known at compile time (static shared-memory offsets; -DWB_JOINTS_INTHREAD=4, experiment)
+template <int kE, int K>
+__device__ __noinline__ void joint_in_thread_static(int col) {
+  Env<1, kE> e;
+  env_for_column(e, shm<kE>(), col, true);
+  constexpr int A = (0x4122 >> (4 * K)) & 0xF, B = (0x3041 >> (4 * K)) & 0xF;
+  joint_step<Env<1, kE>, false>(e, A, K < 2 ? 1 : 2, B, K < 2 ? 4 : 3, nullptr);
+}
 
 // joints (Body, RLU) and (LLU, LLL) -- k = 1, 2 -- touch disjoint bodies: one early-out for both and two independent instruction
 // streams in one function (-DWB_JOINTS_INTHREAD=2)
@@ -1631,7 +1639,12 @@ __global__ void __launch_bounds__(kE, kE == 192 ? 3 : (kE == 160 ? 3 : 512 / kE)
 
 #pragma unroll 1
     for (int it = 0; it < p.iterations; it++) {
-#if WB_JOINTS_INTHREAD == 3
+#if WB_JOINTS_INTHREAD == 4
+      joint_in_thread_static<kE, 0>(tid);
+      joint_in_thread_static<kE, 1>(tid);
+      joint_in_thread_static<kE, 2>(tid);
+      joint_in_thread_static<kE, 3>(tid);
+#elif WB_JOINTS_INTHREAD == 3
       joints_compacted<kE>(tid);
 #elif WB_JOINTS_INTHREAD == 2
       joint_in_thread<kE>(tid, 0);
