@@ -7,7 +7,7 @@ wb = ge.load_package(); wb.init(0)
 from ppo_bipedalwalker_b200._lib import check, lib, ptr
 rng = np.random.default_rng(0)
 ok = True
-for (M, N, K, amn, bmn) in [(128, 64, 64, 0, 0), (64, 64, 64, 0, 0), (64, 64, 64, 2, 2), (64, 128, 16, 2, 2), (64, 64, 64, 2, 3), (64, 64, 64, 0, 3), (64, 64, 64, 3, 3), (64, 72, 64, 3, 3), (128, 16, 64, 3, 3), (128, 8, 64, 3, 3), (64, 64, 32, 2, 0)]:
+for (M, N, K, amn, bmn) in [(128, 64, 64, 0, 0), (64, 64, 64, 0, 0), (64, 64, 64, 2, 2), (64, 128, 16, 2, 2), (64, 64, 64, 2, 3), (64, 64, 64, 0, 3), (64, 64, 64, 3, 3), (64, 72, 64, 3, 3), (128, 16, 64, 3, 3), (128, 8, 64, 3, 3), (64, 64, 32, 2, 0), (64, 128, 16, 0, 2), (64, 64, 64, 0, 2)]:
     for passes in (1, 3):
         A = rng.normal(size=(M, K)).astype(np.float32); B = rng.normal(size=(N, K)).astype(np.float32)
         D = np.zeros((M, N), np.float32)
