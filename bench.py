@@ -476,7 +476,7 @@ def bench_ppo(cx, steps, warmup):
     L = lib()
 
     def one(_):
-        check(L.wb_ppo_train_dev(agent._h, n, *[ptr(t) for t in dev]))  # gradient kernel + fused reduce / Adam kernel
+        check(L.wb_ppo_train_dev(agent._h, n, *[ptr(t) for t in dev]))  # ONE launch: gradient + grid barrier + reduction + Adam
 
     for _ in range(warmup):
         one(0)
