@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # (pytest-timeout registers this one itself where it is installed; without the plug-in the marker is simply inert)
+    config.addinivalue_line("markers", "timeout(seconds): upper bound for one test (pytest-timeout)")
 
 
 @pytest.fixture(scope="session")
