@@ -294,7 +294,8 @@ int32_t wb_ppo_grad_allreduce_dev(wb_policy* p, int32_t n, const float* states_d
 int32_t wb_ppo_train_dev(wb_policy* p, int32_t n, const float* states_dev, const float* actions_dev, const float* old_logp_dev,
                          const float* advantages_dev, const float* returns_dev);
 /* The same on rows index_dev[0..n) of a rollout pool: PPOAgent.CreateBatches (PPOAgent.cs:501-540) fused into the gradient kernel's
- * input prefetch (no gathered copy of the minibatch is written; kernels without that path gather first, as wb_gather_minibatch_dev) */
+ * input prefetch (no gathered copy of the minibatch is written; kernels without that path gather first, as wb_gather_minibatch_dev).
+ * Every index must be a valid row of the pool arrays: the kernel does not range-check device indices. */
 int32_t wb_ppo_train_indexed_dev(wb_policy* p, int32_t n, const int32_t* index_dev, const float* states_pool, const float* actions_pool,
                                  const float* logp_pool, const float* advantages_pool, const float* returns_pool);
 /* PPOAgent.Train(Batch) from host buffers: wb_ppo_grad + wb_adam_step as one call (one launch on the default path).  When all five
